@@ -1,0 +1,189 @@
+/* radarays_b200.h — C ABI of the B200-native RadaRays simulation core (libradarays_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of uos/radarays_ros:
+ *     RadarCPU::simulate(ros::Time)          src/radarays_ros/RadarCPU.cpp:30-564
+ * i.e. per-azimuth beam rays -> multi-bounce closest-hit casts -> Snell/Fresnel + BRDF per bounce ->
+ * range-bin accumulation + denoise/ambient noise -> mono8 polar image (n_cells rows x 400 columns).
+ *
+ * The reference has no FFI; its seam is the C++ virtual `Radar::simulate` (include/radarays_ros/Radar.hpp:64)
+ * chosen in src/radar_simulator.cpp:145-176.  A `RadarB200 : Radar` adapter marshals the
+ * protected state of `Radar` (Radar.hpp:81-105) into the calls below.  Plain pointers and sizes only;
+ * the caller owns every host buffer; every call returns 0 or a negative rr_status and sets
+ * rr_last_error(); calls on one context must be serialised (the reference's single spinner thread).
+ *
+ * There is NO CPU fallback: every entry point that computes needs a CUDA device (sm_100a).
+ */
+#ifndef RADARAYS_B200_H
+#define RADARAYS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_ABI_VERSION 1
+#define RR_N_ANGLES 400            /* Radar.cpp:27-29: theta.size = 400, theta.inc = -(2 pi)/400 */
+
+typedef enum {
+    RR_OK = 0,
+    RR_ERR_INVALID_ARGUMENT = -1,
+    RR_ERR_CUDA = -2,
+    RR_ERR_NOT_READY = -3,         /* mesh / materials / params / samples missing */
+    RR_ERR_OUT_OF_RANGE = -4,      /* material or object id out of bounds (quirk 17 of SURVEY.md) */
+    RR_ERR_WAVE_OVERFLOW = -5,     /* per-azimuth wave list exceeded max_waves_per_azimuth */
+    RR_ERR_NO_DEVICE = -6
+} rr_status;
+
+/* msg/RadarMaterial.msg:1-4 */
+typedef struct { float velocity, ambient, diffuse, specular; } rr_material;
+
+/* msg/RadarModel.msg:1-3 — beam_width in RADIANS (Radar.cpp:213 converts the cfg's degrees) */
+typedef struct { float beam_width; uint32_t n_samples; uint32_t n_reflections; } rr_model;
+
+/* cfg/RadarModel.cfg:11-85 — same names, same order, same defaults (rr_config_defaults) */
+typedef struct {
+    double  z_offset;                          /* unused by RadarCPU */
+    double  range_min;                         /* unused by RadarCPU (quirk 16) */
+    double  range_max;                         /* unused by RadarCPU (quirk 16) */
+    double  beam_width;                        /* degrees */
+    double  resolution;
+    int32_t n_cells;
+    int32_t n_samples;
+    int32_t beam_sample_dist;                  /* 0..3 */
+    double  beam_sample_dist_normal_p_in_cone;
+    int32_t n_reflections;
+    double  energy_min;                        /* unused by RadarCPU */
+    double  energy_max;
+    double  signal_max;
+    int32_t signal_denoising;                  /* 0 none, 1 triangular, 2 gaussian, 3 maxwell-boltzmann */
+    int32_t signal_denoising_triangular_width;
+    double  signal_denoising_triangular_mode;
+    int32_t signal_denoising_gaussian_width;
+    double  signal_denoising_gaussian_mode;
+    int32_t signal_denoising_mb_width;
+    double  signal_denoising_mb_mode;
+    int32_t ambient_noise;                     /* 0 none, 1 uniform, 2 perlin */
+    double  ambient_noise_at_signal_0;
+    double  ambient_noise_at_signal_1;
+    double  ambient_noise_energy_max;
+    double  ambient_noise_energy_min;
+    double  ambient_noise_energy_loss;
+    double  ambient_noise_uniform_max;         /* unused by RadarCPU */
+    double  ambient_noise_perlin_scale_low;    /* unused by RadarCPU (hard-coded 0.05) */
+    double  ambient_noise_perlin_scale_high;   /* unused by RadarCPU (hard-coded 0.2)  */
+    double  ambient_noise_perlin_p_low;        /* unused by RadarCPU (hard-coded 0.9)  */
+    int32_t scroll_image;
+    double  multipath_threshold;
+    int32_t record_multi_reflection;           /* bool */
+    int32_t record_multi_path;                 /* bool */
+    int32_t include_motion;                    /* bool; see rr_simulate_motion */
+} rr_config;
+
+/* Tsm (map <- sensor), Radar.cpp:59-65 */
+typedef struct { float qx, qy, qz, qw, tx, ty, tz; } rr_pose;
+
+/* one closest-hit cast, in the reference's wave-list order (RadarCPU.cpp:243) */
+typedef struct {
+    int32_t  azimuth;
+    int32_t  pass;         /* 0-based pass_id, RadarCPU.cpp:220 */
+    int32_t  face_id;      /* input triangle index, -1 = miss */
+    float    range;        /* Embree tfar equivalent; undefined on miss */
+    float    energy;       /* (float) energy of the traced wave */
+    int32_t  n_children;   /* 0..2 waves pushed for the next pass */
+} rr_cast_record;
+
+/* one radar return, in the order RadarCPU.cpp:322,358 appends them */
+typedef struct {
+    int32_t  azimuth;
+    int32_t  cell;         /* RadarCPU.cpp:413 */
+    float    strength;     /* (float) Signal::strength */
+    float    time;         /* (float) Signal::time */
+} rr_signal_record;
+
+typedef struct {
+    uint64_t n_casts;          /* rays*bounces actually traced in the last call */
+    uint64_t n_hits;
+    uint64_t n_signals;
+    uint64_t nodes_visited;    /* only filled by a stats-enabled call (rr_simulate_stats) */
+    uint64_t tris_tested;      /* idem */
+    uint64_t max_waves;        /* largest per-azimuth wave list seen */
+    uint64_t bvh_nodes;
+    uint64_t bvh_bytes;        /* node array + triangle array */
+    float    kernel_ms;        /* device time of the frame kernel(s), CUDA events */
+    float    bvh_build_ms;
+    int32_t  overflow;         /* 1 if any azimuth hit RR_ERR_WAVE_OVERFLOW */
+} rr_stats;
+
+typedef struct rr_ctx rr_ctx;
+
+int         rr_abi_version(void);
+void        rr_config_defaults(rr_config* cfg);               /* cfg/RadarModel.cfg defaults */
+void        rr_model_defaults(rr_model* model);               /* ros_helper.h:21-28 */
+
+/* replaces: backend construction, radar_simulator.cpp:145-176 */
+int         rr_create(rr_ctx** out, int device_id);
+void        rr_destroy(rr_ctx* ctx);
+const char* rr_last_error(const rr_ctx* ctx);                 /* ctx may be NULL: last creation error */
+
+/* replaces: rm::import_embree_map (radar_simulator.cpp:149); copies, builds the BVH on the device.
+ * tri_object_id (nullable -> all 0) is the Embree geometry/instance id that indexes object_materials
+ * (RadarCPU.cpp:268); one id per face generalises it to per-face materials. */
+int         rr_set_mesh(rr_ctx* ctx, const float* verts_xyz, size_t n_verts,
+                        const uint32_t* tri_idx, size_t n_tris, const uint32_t* tri_object_id);
+
+/* replaces: Radar::loadParams (Radar.cpp:220-226). Bounds-checked (quirk 17). */
+int         rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materials,
+                             const int32_t* object_materials, size_t n_objects, int32_t material_id_air);
+
+/* replaces: Radar::updateDynCfg (Radar.cpp:188-218) + Radar::setParams (Radar.hpp:56-59).
+ * `model` nullable -> derived from cfg exactly as updateDynCfg does. Marks beam samples for resampling
+ * under the same conditions (Radar.cpp:199-206). */
+int         rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg);
+
+/* replaces: sample_cone_local (radar_algorithms.cpp:248-294) cached in m_waves_start (RadarCPU.cpp:136-145).
+ * dirs_xyz nullable -> drawn internally from Philox4x32-10 keyed by (seed, sample). */
+int         rr_set_beam_samples(rr_ctx* ctx, const float* dirs_xyz, size_t n, uint64_t seed);
+int         rr_get_beam_samples(rr_ctx* ctx, float* dirs_xyz_out, size_t capacity, size_t* n_out);
+
+/* replaces: RadarCPU::simulate with include_motion == false, for a batch of poses.
+ * out_polar: n_poses x n_cells x 400 mono8, row-major, row = range bin, col = azimuth (Radar.cpp:34).
+ * frame_id0 + i keys the noise stream of pose i. HOST buffers; copies are part of the call. */
+int         rr_simulate(rr_ctx* ctx, const rr_pose* Tsm, size_t n_poses, uint64_t frame_id0,
+                        uint8_t* out_polar, rr_stats* stats /* nullable */);
+
+/* include_motion == true (RadarCPU.cpp:190-196): one pose PER AZIMUTH, poses[n_frames][400]. */
+int         rr_simulate_motion(rr_ctx* ctx, const rr_pose* Tsm_per_azimuth, size_t n_frames, uint64_t frame_id0,
+                               uint8_t* out_polar, rr_stats* stats /* nullable */);
+
+/* device-resident variant: d_Tsm / d_out_polar are DEVICE pointers, work is enqueued on `cuda_stream`
+ * (a cudaStream_t, NULL = legacy default stream) and NOT synchronised. azimuth_begin/count select a
+ * column shard (multi-GPU azimuth sharding); with column_major != 0 the output is
+ * [pose][azimuth - azimuth_begin][cell] (contiguous per shard), else the full row-major image. */
+int         rr_simulate_device(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64_t frame_id0,
+                               int32_t azimuth_begin, int32_t azimuth_count, int32_t column_major,
+                               int32_t pose_per_azimuth, uint8_t* d_out_polar, void* cuda_stream);
+
+/* same as rr_simulate for ONE pose with traversal counters enabled (nodes_visited / tris_tested). */
+int         rr_simulate_stats(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0, uint8_t* out_polar,
+                              rr_stats* stats);
+
+/* parity probe: per-cast and per-signal records of one frame, in reference order, plus the float
+ * column image BEFORE mono8 quantisation (column-major [azimuth][cell], nullable). */
+int         rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
+                           rr_cast_record* casts, size_t cast_capacity, size_t* n_casts,
+                           rr_signal_record* signals, size_t signal_capacity, size_t* n_signals,
+                           float* columns_f32, uint8_t* out_polar);
+
+/* parity probe for the closest-hit primitive alone (map frame; face id -1 = miss). HOST buffers. */
+int         rr_cast_rays(rr_ctx* ctx, const float* origins_xyz, const float* dirs_xyz, size_t n,
+                         float tmax, int32_t* face_ids, float* ranges);
+
+int         rr_get_stats(rr_ctx* ctx, rr_stats* stats);       /* counters of the last call */
+int         rr_set_max_waves_per_azimuth(rr_ctx* ctx, uint32_t max_waves);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADARAYS_B200_H */
