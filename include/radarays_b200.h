@@ -147,6 +147,10 @@ int         rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* c
 int         rr_set_beam_samples(rr_ctx* ctx, const float* dirs_xyz, size_t n, uint64_t seed);
 int         rr_get_beam_samples(rr_ctx* ctx, float* dirs_xyz_out, size_t capacity, size_t* n_out);
 
+/* seed of the counter-based ambient-noise stream (replaces std::random_device at RadarCPU.cpp:461-462);
+ * draws are keyed by (seed, frame id, azimuth, cell). */
+int         rr_set_noise_seed(rr_ctx* ctx, uint64_t seed);
+
 /* replaces: RadarCPU::simulate with include_motion == false, for a batch of poses.
  * out_polar: n_poses x n_cells x 400 mono8, row-major, row = range bin, col = azimuth (Radar.cpp:34).
  * frame_id0 + i keys the noise stream of pose i. HOST buffers; copies are part of the call. */

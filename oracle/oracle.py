@@ -135,6 +135,11 @@ class OracleScene:
         om = np.ascontiguousarray(sc.object_materials, np.int32)
         dirs = np.ascontiguousarray(beam_dirs, np.float32)
         assert dirs.shape[0] == model.n_samples
+        if not isinstance(poses, C.Array):
+            arr = (Pose * len(poses))()
+            for i, q in enumerate(poses):
+                arr[i] = q
+            poses = arr
         n_poses = len(poses)
         assert n_poses in (1, N_ANGLES)
         img = np.zeros((cfg.n_cells, N_ANGLES), np.uint8)

@@ -1,0 +1,683 @@
+/* rr_api.cu — C ABI of libradarays_b200.so (include/radarays_b200.h). Host side only: context, parameter
+ * marshalling, BVH build dispatch, launches. No CPU implementation of the hot path lives here: every
+ * compute entry point launches rr_kernels.cu and fails loudly without a CUDA device. */
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "rr_bvh.h"
+#include "rr_internal.h"
+
+extern "C" cudaError_t rr_launch_frame(const RRFrameParams* P, int grid, size_t smem, cudaStream_t st, int stats, int debug);
+extern "C" cudaError_t rr_frame_occupancy(int* blocks_per_sm, size_t smem);
+extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
+                                      const float* gs, const float* origins, const float* dirs, size_t n, float tmax,
+                                      int32_t* face_ids, float* ranges, cudaStream_t st);
+int rr_bvh_build_device(const RRTriSoup& soup, RRPackedBVH& out, float* build_ms, std::string& err);   /* rr_bvh_build.cu */
+
+static thread_local std::string g_create_error;
+
+struct rr_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = 0;
+    /* scene */
+    bool have_mesh = false;
+    RRNode* d_nodes = nullptr; float4* d_tris = nullptr;
+    size_t n_nodes = 0, n_tris = 0;
+    uint32_t root_ref = 0; float grid_origin[3], grid_scale[3];
+    float bvh_build_ms = 0.f;
+    uint32_t max_object_id = 0;
+    /* materials */
+    bool have_materials = false;
+    float4* d_materials = nullptr; int32_t* d_object_materials = nullptr;
+    int n_materials = 0, n_objects = 0, air = 0;
+    /* params */
+    bool have_params = false;
+    rr_config cfg; rr_model model;
+    float* d_weights = nullptr; int denoise_width = 0, denoise_mode = 0;
+    /* beam samples */
+    std::vector<float> beam; bool beam_user = false; bool resample = true; uint64_t beam_seed = 0;
+    float* d_beam = nullptr; size_t d_beam_n = 0;
+    float4* d_tas = nullptr;
+    uint64_t noise_seed = 0;
+    uint32_t max_waves_user = 0;
+    /* scratch */
+    int grid = 0; uint32_t wave_cap = 0, sig_cap = 0;
+    float* d_wave_f32 = nullptr; double* d_wave_f64 = nullptr; uint32_t* d_wave_mat = nullptr;
+    int32_t* d_sig_cell = nullptr; float* d_sig_str = nullptr;
+    uint32_t* d_work = nullptr; unsigned long long* d_counters = nullptr; int32_t* d_errflags = nullptr;
+    /* host-buffer path staging */
+    rr_pose* d_poses = nullptr; size_t d_poses_cap = 0;
+    uint8_t* d_out = nullptr; size_t d_out_cap = 0;
+    rr_pose* h_poses = nullptr; size_t h_poses_cap = 0;
+    uint8_t* h_out = nullptr; size_t h_out_cap = 0;
+    rr_stats last{};
+};
+
+static int fail(rr_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, RR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+template <typename T> static cudaError_t regrow(T** p, size_t* cap, size_t need, bool pinned = false)
+{
+    if (need <= *cap) return cudaSuccess;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; }
+    cudaError_t e = pinned ? cudaMallocHost((void**)p, need * sizeof(T)) : cudaMalloc((void**)p, need * sizeof(T));
+    *cap = (e == cudaSuccess) ? need : 0;
+    return e;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * host-side parameter preparation (tiny, once per parameter change): denoiser weights, beam samples, Tas
+ * ------------------------------------------------------------------------------------------------------- */
+namespace {
+
+/* radar_algorithms.h:283-351 + RadarCPU.cpp:48-93 */
+void build_denoise_weights(const rr_config& c, std::vector<float>& w, int& mode)
+{
+    w.clear(); mode = 0;
+    if (c.signal_denoising <= 0) return;
+    int width = 0; double mode_frac = 0.0;
+    if (c.signal_denoising == 1) { width = c.signal_denoising_triangular_width; mode_frac = c.signal_denoising_triangular_mode; }
+    else if (c.signal_denoising == 2) { width = c.signal_denoising_gaussian_width; mode_frac = c.signal_denoising_gaussian_mode; }
+    else if (c.signal_denoising == 3) { width = c.signal_denoising_mb_width; mode_frac = c.signal_denoising_mb_mode; }
+    else return;
+    mode = (int)(mode_frac * width);
+    w.resize(width);
+    if (c.signal_denoising == 3) {
+        const float a = (float)((float)mode / M_SQRT2);
+        const float aa = a * a, aaa = a * a * a;
+        for (int i = 0; i < width; i++) {
+            const float x = (float)i, xx = x * x;
+            w[i] = (float)(std::sqrt(2.0 / M_PI) * xx * std::exp(-xx / (2 * aa)) / aaa);
+        }
+    } else {   /* triangular; the reference's "gaussian" is the same triangle (radar_algorithms.h:310-335) */
+        for (int i = 0; i < width; i++) {
+            float p;
+            if (i <= mode) p = (float)i / (float)mode;
+            else p = (float)(1.0 - (((float)i - (float)mode) / ((float)width - (float)mode)));
+            w[i] = p;
+        }
+    }
+    float sum = 0.0f;
+    for (float v : w) sum += v;
+    for (float& v : w) v /= sum;
+    if (!w.empty()) {
+        const double mv = w[mode];
+        for (float& v : w) v = (float)(v / mv);
+    }
+}
+
+/* radar_math.h:13-44 (single-precision erfinv, Giles-style polynomial) */
+float erfinv_f32(float a)
+{
+    float t = logf(fmaf(a, 0.0f - a, 1.0f));
+    float p;
+    if (fabsf(t) > 6.125f) {
+        const float k[9] = {3.03697567e-10f, 2.93243101e-8f, 1.22150334e-6f, 2.84108955e-5f, 3.93552968e-4f,
+                            3.02698812e-3f, 4.83185798e-3f, -2.64646143e-1f, 8.40016484e-1f};
+        p = k[0];
+        for (int i = 1; i < 9; i++) p = fmaf(p, t, k[i]);
+    } else {
+        const float k[10] = {5.43877832e-9f, 1.43285448e-7f, 1.22774793e-6f, 1.12963626e-7f, -5.61530760e-5f,
+                             -1.47697632e-4f, 2.31468678e-3f, 1.15392581e-2f, -2.32015476e-1f, 8.86226892e-1f};
+        p = k[0];
+        for (int i = 1; i < 10; i++) p = fmaf(p, t, k[i]);
+    }
+    return a * p;
+}
+
+rr_quat euler_to_quat(float roll, float pitch, float yaw)     /* rmagine EulerAngles -> Quaternion (ZYX) */
+{
+    const float cr = cosf(roll / 2.0f), sr = sinf(roll / 2.0f);
+    const float cp = cosf(pitch / 2.0f), sp = sinf(pitch / 2.0f);
+    const float cy = cosf(yaw / 2.0f), sy = sinf(yaw / 2.0f);
+    rr_quat q;
+    q.w = cr * cp * cy + sr * sp * sy;
+    q.x = sr * cp * cy - cr * sp * sy;
+    q.y = cr * sp * cy + sr * cp * sy;
+    q.z = cr * cp * sy - sr * sp * cy;
+    return q;
+}
+
+/* sample_cone_local (radar_algorithms.cpp:248-294) with Philox4x32-10 keyed by (seed, sample) in place of
+ * std::mt19937(random_device): word0 -> angle, word1 -> radius, word2 -> normal via radar_math.h:47-50. */
+void draw_beam_samples(float width, int n, int dist, float p_in_cone, uint64_t seed, std::vector<float>& out)
+{
+    out.resize((size_t)3 * n);
+    const float z = (float)(M_SQRT2 * erfinv_f32(p_in_cone));
+    const float radius = (float)(width / 2.0);
+    for (int i = 0; i < n; i++) {
+        const uint32_t ctr[4] = {(uint32_t)i, 0u, 0u, 0x52524253u};
+        const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t r[4];
+        rr_philox4x32_10(ctr, key, r);
+        const float ua = rr_u01(r[0]), ur = rr_u01(r[1]);
+        const float un = ((float)(r[2] >> 9) + 0.5f) * 0x1p-23f;
+        const float gauss = (float)(M_SQRT2 * erfinv_f32((float)(2 * un - 1.0)));
+        const float ang = (float)(ua * 2.0f * M_PI - M_PI);
+        float rad = 0.f;
+        switch (dist) {
+            case 0: rad = ur * radius; break;
+            case 1: rad = sqrtf(ur) * radius; break;
+            case 2: rad = (gauss / z) * radius; break;
+            case 3: rad = sqrtf(fabsf(gauss) / z) * radius; break;
+            default: break;
+        }
+        const float alpha = rad * cosf(ang), beta = rad * sinf(ang);
+        const rr_vec3 d = rr_qrot(euler_to_quat(0.f, alpha, beta), rr_v3(1.f, 0.f, 0.f));
+        out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+    }
+}
+
+} // namespace
+
+/* ---------------------------------------------------------------------------------------------------------*/
+extern "C" {
+
+int rr_abi_version(void) { return RR_ABI_VERSION; }
+
+void rr_config_defaults(rr_config* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->z_offset = 0.0; c->range_min = 0.0; c->range_max = 600.0; c->beam_width = 8.0; c->resolution = 0.0438;
+    c->n_cells = 3424; c->n_samples = 10; c->beam_sample_dist = 2; c->beam_sample_dist_normal_p_in_cone = 0.8;
+    c->n_reflections = 4; c->energy_min = 0.0; c->energy_max = 0.5; c->signal_max = 120.0;
+    c->signal_denoising = 1;
+    c->signal_denoising_triangular_width = 50; c->signal_denoising_triangular_mode = 0.35;
+    c->signal_denoising_gaussian_width = 50; c->signal_denoising_gaussian_mode = 0.5;
+    c->signal_denoising_mb_width = 50; c->signal_denoising_mb_mode = 0.4;
+    c->ambient_noise = 2; c->ambient_noise_at_signal_0 = 0.3; c->ambient_noise_at_signal_1 = 0.03;
+    c->ambient_noise_energy_max = 0.5; c->ambient_noise_energy_min = 0.1; c->ambient_noise_energy_loss = 0.05;
+    c->ambient_noise_uniform_max = 0.15; c->ambient_noise_perlin_scale_low = 0.05;
+    c->ambient_noise_perlin_scale_high = 0.2; c->ambient_noise_perlin_p_low = 0.9;
+    c->scroll_image = 0; c->multipath_threshold = 0.5; c->record_multi_reflection = 1; c->record_multi_path = 0;
+    c->include_motion = 1;
+}
+
+void rr_model_defaults(rr_model* m)
+{
+    m->beam_width = (float)(8.0 * M_PI / 180.0); m->n_samples = 200; m->n_reflections = 2;
+}
+
+const char* rr_last_error(const rr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rr_create(rr_ctx** out, int device_id)
+{
+    rr_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, RR_ERR_INVALID_ARGUMENT, "rr_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, RR_ERR_NO_DEVICE, "rr_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n_dev) return fail(nullptr, RR_ERR_INVALID_ARGUMENT, "rr_create: device %d of %d", device_id, n_dev);
+    ctx = new rr_ctx();
+    ctx->device = device_id;
+    auto bail = [&](cudaError_t er, const char* what) { fail(nullptr, RR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(er)); delete ctx; return RR_ERR_CUDA; };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    ctx->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    if ((e = cudaMalloc((void**)&ctx->d_work, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&ctx->d_errflags, 4 * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&ctx->d_tas, RR_N_ANGLES * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&ctx->d_weights, RR_MAX_DENOISE * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
+    /* Tas.R for the 400 azimuths: EulerAngles{0,0,theta(a)}, theta = 0 + a * float(-(2 pi)/400) (Radar.cpp:27-28, RadarCPU.cpp:201-203) */
+    std::vector<float4> tas(RR_N_ANGLES);
+    const float theta_inc = (float)(-(2 * M_PI) / 400);
+    for (int a = 0; a < RR_N_ANGLES; a++) {
+        const rr_quat q = euler_to_quat(0.0f, 0.0f, 0.0f + (float)a * theta_inc);
+        tas[a] = make_float4(q.x, q.y, q.z, q.w);
+    }
+    if ((e = cudaMemcpy(ctx->d_tas, tas.data(), tas.size() * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    rr_config_defaults(&ctx->cfg);
+    *out = ctx;
+    return RR_OK;
+}
+
+void rr_destroy(rr_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials);
+    cudaFree(ctx->d_weights); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
+    cudaFree(ctx->d_wave_f32); cudaFree(ctx->d_wave_f64); cudaFree(ctx->d_wave_mat);
+    cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_counters); cudaFree(ctx->d_errflags);
+    cudaFree(ctx->d_poses); cudaFree(ctx->d_out);
+    if (ctx->h_poses) cudaFreeHost(ctx->h_poses);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t* tri_idx, size_t n_tris,
+                const uint32_t* tri_object_id)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    if ((n_tris && (!verts || !tri_idx)) || n_tris >= (1u << 28))
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: bad arguments (n_tris=%zu, limit 2^28)", n_tris);
+    CK(cudaSetDevice(ctx->device));
+    RRTriSoup soup;
+    soup.v0.resize(n_tris); soup.e1.resize(n_tris); soup.e2.resize(n_tris); soup.obj.resize(n_tris);
+    uint32_t max_obj = 0;
+    for (size_t f = 0; f < n_tris; f++) {
+        const uint32_t a = tri_idx[3 * f], b = tri_idx[3 * f + 1], c = tri_idx[3 * f + 2];
+        if (a >= n_verts || b >= n_verts || c >= n_verts)
+            return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: face %zu references a vertex >= n_verts", f);
+        const rr_vec3 A = rr_v3(verts[3 * a], verts[3 * a + 1], verts[3 * a + 2]);
+        const rr_vec3 B = rr_v3(verts[3 * b], verts[3 * b + 1], verts[3 * b + 2]);
+        const rr_vec3 Cc = rr_v3(verts[3 * c], verts[3 * c + 1], verts[3 * c + 2]);
+        soup.v0[f] = A; soup.e1[f] = rr_sub(B, A); soup.e2[f] = rr_sub(Cc, A);
+        soup.obj[f] = tri_object_id ? tri_object_id[f] : 0u;
+        if (soup.obj[f] > max_obj) max_obj = soup.obj[f];
+    }
+    RRPackedBVH bvh;
+    float build_ms = 0.f;
+    std::string berr;
+    const int rc = rr_bvh_build_device(soup, bvh, &build_ms, berr);
+    if (rc != RR_OK) return fail(ctx, rc, "rr_set_mesh: BVH build failed: %s", berr.c_str());
+    cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); ctx->d_nodes = nullptr; ctx->d_tris = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(RRNode)));
+    CK(cudaMalloc((void**)&ctx->d_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(float4)));
+    CK(cudaMemcpy(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(RRNode), cudaMemcpyHostToDevice));
+    if (!bvh.tris.empty()) CK(cudaMemcpy(ctx->d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    ctx->n_nodes = bvh.nodes.size(); ctx->n_tris = n_tris; ctx->root_ref = bvh.root_ref;
+    memcpy(ctx->grid_origin, bvh.grid_origin, sizeof(ctx->grid_origin));
+    memcpy(ctx->grid_scale, bvh.grid_scale, sizeof(ctx->grid_scale));
+    ctx->bvh_build_ms = build_ms;
+    ctx->max_object_id = max_obj;
+    ctx->have_mesh = true;
+    return RR_OK;
+}
+
+int rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materials,
+                     const int32_t* object_materials, size_t n_objects, int32_t material_id_air)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    if (!materials || !n_materials || !object_materials || !n_objects)
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_materials: empty tables");
+    if (material_id_air < 0 || (size_t)material_id_air >= n_materials)
+        return fail(ctx, RR_ERR_OUT_OF_RANGE, "rr_set_materials: material_id_air %d outside [0,%zu)", material_id_air, n_materials);
+    for (size_t o = 0; o < n_objects; o++)
+        if (object_materials[o] < 0 || (size_t)object_materials[o] >= n_materials)
+            return fail(ctx, RR_ERR_OUT_OF_RANGE, "rr_set_materials: object_materials[%zu] = %d outside [0,%zu)", o, object_materials[o], n_materials);
+    CK(cudaSetDevice(ctx->device));
+    std::vector<float4> m(n_materials);
+    for (size_t i = 0; i < n_materials; i++) m[i] = make_float4(materials[i].velocity, materials[i].ambient, materials[i].diffuse, materials[i].specular);
+    cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials); ctx->d_materials = nullptr; ctx->d_object_materials = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_materials, n_materials * sizeof(float4)));
+    CK(cudaMalloc((void**)&ctx->d_object_materials, n_objects * sizeof(int32_t)));
+    CK(cudaMemcpy(ctx->d_materials, m.data(), n_materials * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_object_materials, object_materials, n_objects * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->n_materials = (int)n_materials; ctx->n_objects = (int)n_objects; ctx->air = material_id_air;
+    ctx->have_materials = true;
+    return RR_OK;
+}
+
+int rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg)
+{
+    if (!ctx || !cfg) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_params: cfg is NULL");
+    if (cfg->n_cells < 1 || cfg->n_cells > 10000) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "n_cells %d outside [1,10000]", cfg->n_cells);
+    const int dn = cfg->signal_denoising;
+    const int width = dn == 1 ? cfg->signal_denoising_triangular_width : dn == 2 ? cfg->signal_denoising_gaussian_width
+                    : dn == 3 ? cfg->signal_denoising_mb_width : 1;
+    if (dn < 0 || dn > 3 || width < 1 || width > 200) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "signal_denoising %d / width %d invalid", dn, width);
+    if (cfg->ambient_noise < 0 || cfg->ambient_noise > 2) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "ambient_noise %d invalid", cfg->ambient_noise);
+    if (!(cfg->resolution > 0.0)) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "resolution must be > 0");
+    rr_model m;
+    if (model) m = *model;
+    else {   /* Radar.cpp:209-215 */
+        m.beam_width = (float)(cfg->beam_width * M_PI / 180.0);
+        m.n_samples = (uint32_t)cfg->n_samples;
+        m.n_reflections = (uint32_t)cfg->n_reflections;
+    }
+    if (m.n_samples < 1 || m.n_samples > 65535) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "n_samples %u outside [1,65535]", m.n_samples);
+    if (m.n_reflections > 20) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "n_reflections %u > 20", m.n_reflections);
+    CK(cudaSetDevice(ctx->device));
+    /* Radar.cpp:199-206: which changes invalidate the cached beam samples */
+    if (!ctx->have_params || cfg->beam_sample_dist != ctx->cfg.beam_sample_dist
+        || std::fabs(cfg->beam_width - ctx->cfg.beam_width) > 0.001 || cfg->n_samples != ctx->cfg.n_samples
+        || std::fabs(cfg->beam_sample_dist_normal_p_in_cone - ctx->cfg.beam_sample_dist_normal_p_in_cone) > 0.001
+        || m.n_samples != ctx->model.n_samples || m.beam_width != ctx->model.beam_width)
+        ctx->resample = true;
+    ctx->cfg = *cfg; ctx->model = m;
+    std::vector<float> w; int mode = 0;
+    build_denoise_weights(*cfg, w, mode);
+    if (dn > 0 && (mode < 0 || mode >= (int)w.size())) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "denoising mode index %d outside kernel width %zu", mode, w.size());
+    std::vector<float> wpad(RR_MAX_DENOISE, 0.f);
+    std::copy(w.begin(), w.end(), wpad.begin());
+    CK(cudaMemcpy(ctx->d_weights, wpad.data(), RR_MAX_DENOISE * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->denoise_width = (int)w.size(); ctx->denoise_mode = mode;
+    ctx->have_params = true;
+    return RR_OK;
+}
+
+int rr_set_noise_seed(rr_ctx* ctx, uint64_t seed) { if (!ctx) return RR_ERR_INVALID_ARGUMENT; ctx->noise_seed = seed; return RR_OK; }
+
+int rr_set_max_waves_per_azimuth(rr_ctx* ctx, uint32_t max_waves)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    ctx->max_waves_user = max_waves;
+    return RR_OK;
+}
+
+static int upload_beam(rr_ctx* ctx)
+{
+    const size_t n = ctx->beam.size() / 3;
+    if (n > ctx->d_beam_n) {
+        cudaFree(ctx->d_beam); ctx->d_beam = nullptr; ctx->d_beam_n = 0;
+        CK(cudaMalloc((void**)&ctx->d_beam, n * 3 * sizeof(float)));
+        ctx->d_beam_n = n;
+    }
+    CK(cudaMemcpy(ctx->d_beam, ctx->beam.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    return RR_OK;
+}
+
+int rr_set_beam_samples(rr_ctx* ctx, const float* dirs_xyz, size_t n, uint64_t seed)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    ctx->beam_seed = seed;
+    if (dirs_xyz) {
+        if (n < 1 || n > 65535) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_beam_samples: n %zu outside [1,65535]", n);
+        ctx->beam.assign(dirs_xyz, dirs_xyz + 3 * n);
+        ctx->beam_user = true; ctx->resample = false;
+        return upload_beam(ctx);
+    }
+    ctx->beam_user = false; ctx->resample = true;      /* drawn when the parameters are known */
+    return RR_OK;
+}
+
+static int ensure_beam(rr_ctx* ctx)
+{
+    const size_t want = ctx->model.n_samples;
+    if (ctx->beam_user && ctx->beam.size() / 3 == want) return RR_OK;      /* caller-supplied m_waves_start */
+    if (!ctx->resample && ctx->beam.size() / 3 == want) return RR_OK;
+    draw_beam_samples(ctx->model.beam_width, (int)want, ctx->cfg.beam_sample_dist,
+                      (float)ctx->cfg.beam_sample_dist_normal_p_in_cone, ctx->beam_seed, ctx->beam);
+    ctx->beam_user = false; ctx->resample = false;
+    return upload_beam(ctx);
+}
+
+int rr_get_beam_samples(rr_ctx* ctx, float* out, size_t capacity, size_t* n_out)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_params) return fail(ctx, RR_ERR_NOT_READY, "rr_get_beam_samples: rr_set_params first");
+    const int rc = ensure_beam(ctx);
+    if (rc) return rc;
+    const size_t n = ctx->beam.size() / 3;
+    if (n_out) *n_out = n;
+    if (out) {
+        if (capacity < n) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_get_beam_samples: capacity %zu < %zu", capacity, n);
+        memcpy(out, ctx->beam.data(), n * 3 * sizeof(float));
+    }
+    return RR_OK;
+}
+
+/* ---- launch plumbing ------------------------------------------------------------------------------------*/
+static int ready(rr_ctx* ctx)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_mesh) return fail(ctx, RR_ERR_NOT_READY, "no mesh: call rr_set_mesh");
+    if (!ctx->have_materials) return fail(ctx, RR_ERR_NOT_READY, "no materials: call rr_set_materials");
+    if (!ctx->have_params) return fail(ctx, RR_ERR_NOT_READY, "no parameters: call rr_set_params");
+    if (ctx->max_object_id >= (uint32_t)ctx->n_objects)
+        return fail(ctx, RR_ERR_OUT_OF_RANGE, "mesh uses object id %u but object_materials has %d entries", ctx->max_object_id, ctx->n_objects);
+    CK(cudaSetDevice(ctx->device));
+    return ensure_beam(ctx);
+}
+
+static int ensure_scratch(rr_ctx* ctx)
+{
+    const size_t smem = (size_t)ctx->cfg.n_cells * sizeof(float);
+    int per_sm = 0;
+    CK(rr_frame_occupancy(&per_sm, smem));
+    if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "frame kernel does not fit on an SM (smem %zu)", smem);
+    const int grid = ctx->num_sms * per_sm;
+    const uint32_t S = ctx->model.n_samples, Pn = ctx->model.n_reflections;
+    uint32_t cap = ctx->max_waves_user;
+    if (cap == 0) {   /* default: room for 3 dielectric splits per sample path */
+        const uint32_t growth = 1u << std::min<uint32_t>(Pn > 0 ? Pn - 1 : 0, 3);
+        cap = S * growth;
+    }
+    cap = std::max<uint32_t>(cap, S);
+    cap = (cap + 31u) & ~31u;
+    const uint32_t scap = 2u * cap * std::max<uint32_t>(1, std::min<uint32_t>(Pn, 4));
+    if (grid != ctx->grid || cap != ctx->wave_cap || scap != ctx->sig_cap) {
+        cudaFree(ctx->d_wave_f32); cudaFree(ctx->d_wave_f64); cudaFree(ctx->d_wave_mat); cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str);
+        ctx->d_wave_f32 = nullptr; ctx->d_wave_f64 = nullptr; ctx->d_wave_mat = nullptr; ctx->d_sig_cell = nullptr; ctx->d_sig_str = nullptr;
+        ctx->grid = 0;
+        CK(cudaMalloc((void**)&ctx->d_wave_f32, (size_t)grid * 2 * 6 * cap * sizeof(float)));
+        CK(cudaMalloc((void**)&ctx->d_wave_f64, (size_t)grid * 2 * 2 * cap * sizeof(double)));
+        CK(cudaMalloc((void**)&ctx->d_wave_mat, (size_t)grid * 2 * cap * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&ctx->d_sig_cell, (size_t)grid * scap * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&ctx->d_sig_str, (size_t)grid * scap * sizeof(float)));
+        ctx->grid = grid; ctx->wave_cap = cap; ctx->sig_cap = scap;
+    }
+    return RR_OK;
+}
+
+static void fill_params(rr_ctx* ctx, RRFrameParams& P)
+{
+    memset(&P, 0, sizeof(P));
+    const rr_config& c = ctx->cfg;
+    P.nodes = ctx->d_nodes; P.tris = ctx->d_tris; P.root_ref = ctx->root_ref;
+    for (int a = 0; a < 3; a++) { P.grid_origin[a] = ctx->grid_origin[a]; P.grid_scale[a] = ctx->grid_scale[a]; }
+    P.materials = ctx->d_materials; P.object_materials = ctx->d_object_materials;
+    P.n_materials = ctx->n_materials; P.n_objects = ctx->n_objects; P.material_id_air = ctx->air;
+    P.beam_dirs = ctx->d_beam; P.tas_quat = ctx->d_tas;
+    P.n_samples = (int)ctx->model.n_samples; P.n_passes = (int)ctx->model.n_reflections;
+    P.n_cells = c.n_cells; P.scroll_image = c.scroll_image; P.resolution = c.resolution;
+    P.energy_max_f = (float)c.energy_max; P.signal_max = c.signal_max;
+    P.denoise_on = c.signal_denoising > 0 ? 1 : 0; P.denoise_width = ctx->denoise_width; P.denoise_mode = ctx->denoise_mode;
+    P.denoise_weights = ctx->d_weights;
+    P.ambient_noise = c.ambient_noise;
+    P.noise_at_signal_0 = c.ambient_noise_at_signal_0; P.noise_at_signal_1 = c.ambient_noise_at_signal_1;
+    P.noise_energy_max = c.ambient_noise_energy_max; P.noise_energy_min = c.ambient_noise_energy_min;
+    P.noise_energy_loss = c.ambient_noise_energy_loss;
+    P.record_multi_reflection = c.record_multi_reflection; P.record_multi_path = c.record_multi_path;
+    P.multipath_threshold = c.multipath_threshold;
+    P.noise_seed = ctx->noise_seed;
+    P.wave_f32 = ctx->d_wave_f32; P.wave_f64 = ctx->d_wave_f64; P.wave_mat = ctx->d_wave_mat;
+    P.sig_cell = ctx->d_sig_cell; P.sig_strength = ctx->d_sig_str; P.wave_cap = ctx->wave_cap; P.sig_cap = ctx->sig_cap;
+    P.work_counter = ctx->d_work; P.counters = ctx->d_counters; P.error_flags = ctx->d_errflags;
+}
+
+static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, int debug)
+{
+    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_errflags, 0, 4 * sizeof(int32_t), st));
+    const uint32_t items = (uint32_t)P.n_poses * (uint32_t)P.az_count;
+    const int grid = (int)std::min<uint32_t>((uint32_t)ctx->grid, std::max<uint32_t>(items, 1));
+    CK(rr_launch_frame(&P, grid, (size_t)P.n_cells * sizeof(float), st, stats, debug));
+    return RR_OK;
+}
+
+static int collect(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
+{
+    unsigned long long cnt[8]; int32_t flags[4];
+    CK(cudaMemcpy(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(flags, ctx->d_errflags, sizeof(flags), cudaMemcpyDeviceToHost));
+    rr_stats& s = ctx->last;
+    s.n_casts = cnt[0]; s.n_hits = cnt[1]; s.n_signals = cnt[2]; s.nodes_visited = cnt[3]; s.tris_tested = cnt[4];
+    s.max_waves = cnt[5]; s.bvh_nodes = ctx->n_nodes;
+    s.bvh_bytes = ctx->n_nodes * sizeof(RRNode) + ctx->n_tris * 3 * sizeof(float4);
+    s.kernel_ms = kernel_ms; s.bvh_build_ms = ctx->bvh_build_ms; s.overflow = flags[0];
+    if (stats) *stats = s;
+    if (flags[1]) return fail(ctx, RR_ERR_OUT_OF_RANGE, "a hit face carries an object id >= n_objects");
+    if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave/signal list overflow (cap %u waves per azimuth); raise rr_set_max_waves_per_azimuth", ctx->wave_cap);
+    return RR_OK;
+}
+
+static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int per_az, uint64_t frame_id0,
+                         uint8_t* out_polar, rr_stats* stats, int with_stats)
+{
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!poses || !out_polar || n_frames == 0) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "simulate: NULL buffers or zero poses");
+    if ((rc = ensure_scratch(ctx))) return rc;
+    const size_t n_pose_structs = n_frames * (per_az ? RR_N_ANGLES : 1);
+    const size_t img = (size_t)ctx->cfg.n_cells * RR_N_ANGLES;
+    CK(regrow(&ctx->d_poses, &ctx->d_poses_cap, n_pose_structs));
+    CK(regrow(&ctx->d_out, &ctx->d_out_cap, n_frames * img));
+    CK(regrow(&ctx->h_poses, &ctx->h_poses_cap, n_pose_structs, true));
+    CK(regrow(&ctx->h_out, &ctx->h_out_cap, n_frames * img, true));
+    memcpy(ctx->h_poses, poses, n_pose_structs * sizeof(rr_pose));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_poses, ctx->h_poses, n_pose_structs * sizeof(rr_pose), cudaMemcpyHostToDevice, st));
+    RRFrameParams P;
+    fill_params(ctx, P);
+    P.poses = ctx->d_poses; P.n_poses = (int)n_frames; P.pose_per_azimuth = per_az;
+    P.az_begin = 0; P.az_count = RR_N_ANGLES; P.frame_id0 = frame_id0;
+    P.out = ctx->d_out; P.column_major = 0;
+    CK(cudaEventRecord(ctx->ev0, st));
+    if ((rc = enqueue(ctx, P, st, with_stats, 0))) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, n_frames * img, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out_polar, ctx->h_out, n_frames * img);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    return collect(ctx, stats, ms);
+}
+
+int rr_simulate(rr_ctx* ctx, const rr_pose* Tsm, size_t n_poses, uint64_t frame_id0, uint8_t* out_polar, rr_stats* stats)
+{
+    return simulate_host(ctx, Tsm, n_poses, 0, frame_id0, out_polar, stats, 0);
+}
+
+int rr_simulate_motion(rr_ctx* ctx, const rr_pose* Tsm_per_azimuth, size_t n_frames, uint64_t frame_id0,
+                       uint8_t* out_polar, rr_stats* stats)
+{
+    return simulate_host(ctx, Tsm_per_azimuth, n_frames, 1, frame_id0, out_polar, stats, 0);
+}
+
+int rr_simulate_stats(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0, uint8_t* out_polar, rr_stats* stats)
+{
+    return simulate_host(ctx, Tsm, 1, 0, frame_id0, out_polar, stats, 1);
+}
+
+int rr_simulate_device(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64_t frame_id0,
+                       int32_t azimuth_begin, int32_t azimuth_count, int32_t column_major,
+                       int32_t pose_per_azimuth, uint8_t* d_out_polar, void* cuda_stream)
+{
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!d_Tsm || !d_out_polar || n_poses == 0) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_device: NULL buffers or zero poses");
+    if (azimuth_begin < 0 || azimuth_count < 1 || azimuth_begin + azimuth_count > RR_N_ANGLES)
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_device: azimuth shard [%d,%d) outside [0,400)", azimuth_begin, azimuth_begin + azimuth_count);
+    if ((rc = ensure_scratch(ctx))) return rc;
+    RRFrameParams P;
+    fill_params(ctx, P);
+    P.poses = d_Tsm; P.n_poses = (int)n_poses; P.pose_per_azimuth = pose_per_azimuth ? 1 : 0;
+    P.az_begin = azimuth_begin; P.az_count = azimuth_count; P.frame_id0 = frame_id0;
+    P.out = d_out_polar; P.column_major = column_major ? 1 : 0;
+    return enqueue(ctx, P, (cudaStream_t)cuda_stream, 0, 0);
+}
+
+int rr_get_stats(rr_ctx* ctx, rr_stats* stats)
+{
+    if (!ctx || !stats) return RR_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    return collect(ctx, stats, ctx->last.kernel_ms);
+}
+
+int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
+                   rr_cast_record* casts, size_t cast_capacity, size_t* n_casts,
+                   rr_signal_record* signals, size_t signal_capacity, size_t* n_signals,
+                   float* columns_f32, uint8_t* out_polar)
+{
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!Tsm) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_debug_trace: NULL pose");
+    if ((rc = ensure_scratch(ctx))) return rc;
+    const uint32_t Pn = std::max<uint32_t>(1, ctx->model.n_reflections);
+    const uint32_t ccap = ctx->wave_cap * Pn, scap = ctx->sig_cap;
+    const int C = ctx->cfg.n_cells;
+    rr_cast_record* d_casts = nullptr; rr_signal_record* d_sigs = nullptr; uint32_t* d_cnt = nullptr; float* d_cols = nullptr;
+    rr_pose* d_pose = nullptr; uint8_t* d_img = nullptr;
+    auto cleanup = [&]() { cudaFree(d_casts); cudaFree(d_sigs); cudaFree(d_cnt); cudaFree(d_cols); cudaFree(d_pose); cudaFree(d_img); };
+#define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    CKD(cudaMalloc((void**)&d_casts, (size_t)RR_N_ANGLES * ccap * sizeof(rr_cast_record)));
+    CKD(cudaMalloc((void**)&d_sigs, (size_t)RR_N_ANGLES * scap * sizeof(rr_signal_record)));
+    CKD(cudaMalloc((void**)&d_cnt, (size_t)RR_N_ANGLES * 2 * sizeof(uint32_t)));
+    CKD(cudaMalloc((void**)&d_cols, (size_t)RR_N_ANGLES * C * sizeof(float)));
+    CKD(cudaMalloc((void**)&d_pose, sizeof(rr_pose)));
+    CKD(cudaMalloc((void**)&d_img, (size_t)C * RR_N_ANGLES));
+    CKD(cudaMemset(d_cnt, 0, (size_t)RR_N_ANGLES * 2 * sizeof(uint32_t)));
+    CKD(cudaMemcpy(d_pose, Tsm, sizeof(rr_pose), cudaMemcpyHostToDevice));
+    RRFrameParams P;
+    fill_params(ctx, P);
+    P.poses = d_pose; P.n_poses = 1; P.pose_per_azimuth = 0; P.az_begin = 0; P.az_count = RR_N_ANGLES;
+    P.frame_id0 = frame_id0; P.out = d_img; P.column_major = 0;
+    P.dbg_casts = d_casts; P.dbg_signals = d_sigs; P.dbg_counts = d_cnt; P.dbg_columns = d_cols;
+    P.dbg_cast_cap = ccap; P.dbg_sig_cap = scap;
+    if ((rc = enqueue(ctx, P, ctx->stream, 1, 1))) { cleanup(); return rc; }
+    CKD(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> cnt(RR_N_ANGLES * 2);
+    CKD(cudaMemcpy(cnt.data(), d_cnt, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    size_t nc = 0, ns = 0;
+    for (int a = 0; a < RR_N_ANGLES; a++) {
+        const size_t c = std::min<size_t>(cnt[2 * a], ccap), s = std::min<size_t>(cnt[2 * a + 1], scap);
+        if (casts && nc + c <= cast_capacity) CKD(cudaMemcpy(casts + nc, d_casts + (size_t)a * ccap, c * sizeof(rr_cast_record), cudaMemcpyDeviceToHost));
+        if (signals && ns + s <= signal_capacity) CKD(cudaMemcpy(signals + ns, d_sigs + (size_t)a * scap, s * sizeof(rr_signal_record), cudaMemcpyDeviceToHost));
+        nc += c; ns += s;
+    }
+    if (n_casts) *n_casts = nc;
+    if (n_signals) *n_signals = ns;
+    if (columns_f32) CKD(cudaMemcpy(columns_f32, d_cols, (size_t)RR_N_ANGLES * C * sizeof(float), cudaMemcpyDeviceToHost));
+    if (out_polar) CKD(cudaMemcpy(out_polar, d_img, (size_t)C * RR_N_ANGLES, cudaMemcpyDeviceToHost));
+    cleanup();
+#undef CKD
+    return collect(ctx, nullptr, 0.f);
+}
+
+int rr_cast_rays(rr_ctx* ctx, const float* origins, const float* dirs, size_t n, float tmax, int32_t* face_ids, float* ranges)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_mesh) return fail(ctx, RR_ERR_NOT_READY, "no mesh: call rr_set_mesh");
+    if (n == 0) return RR_OK;
+    if (!origins || !dirs || !face_ids || !ranges) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_cast_rays: NULL buffers");
+    CK(cudaSetDevice(ctx->device));
+    float *d_o = nullptr, *d_d = nullptr, *d_r = nullptr; int32_t* d_f = nullptr;
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_r); cudaFree(d_f); };
+#define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    CKD(cudaMalloc((void**)&d_o, n * 3 * sizeof(float)));
+    CKD(cudaMalloc((void**)&d_d, n * 3 * sizeof(float)));
+    CKD(cudaMalloc((void**)&d_r, n * sizeof(float)));
+    CKD(cudaMalloc((void**)&d_f, n * sizeof(int32_t)));
+    CKD(cudaMemcpy(d_o, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    CKD(cudaMemcpy(d_d, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    CKD(rr_launch_cast(ctx->d_nodes, ctx->d_tris, ctx->root_ref, ctx->grid_origin, ctx->grid_scale, d_o, d_d, n, tmax, d_f, d_r, ctx->stream));
+    CKD(cudaStreamSynchronize(ctx->stream));
+    CKD(cudaMemcpy(face_ids, d_f, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(ranges, d_r, n * sizeof(float), cudaMemcpyDeviceToHost));
+    cleanup();
+#undef CKD
+    return RR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,191 @@
+/* rr_bvh.cpp — host binned-SAH builder + packing into the 32-byte quantised node format.
+ * Replaces what rm::import_embree_map builds inside Embree (call site src/radar_simulator.cpp:149). */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "rr_bvh.h"
+
+namespace {
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; } }
+    void grow(const float* l, const float* h) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); } }
+    void grow(const Box& b) { grow(b.lo, b.hi); }
+    float half_area() const
+    {
+        const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return (x < 0.f) ? 0.f : (x * y + y * z + z * x);
+    }
+};
+constexpr int NB = 16;
+}
+
+void rr_bvh_build_host(const RRTriSoup& soup, std::vector<RRBuildNode>& nodes, std::vector<uint32_t>& order)
+{
+    const size_t n = soup.v0.size();
+    std::vector<float> blo(3 * n), bhi(3 * n), cen(3 * n);
+    order.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        order[i] = (uint32_t)i;
+        const rr_vec3 a = soup.v0[i], b = rr_add(soup.v0[i], soup.e1[i]), c = rr_add(soup.v0[i], soup.e2[i]);
+        const float xs[3] = {a.x, b.x, c.x}, ys[3] = {a.y, b.y, c.y}, zs[3] = {a.z, b.z, c.z};
+        blo[3 * i + 0] = std::min({xs[0], xs[1], xs[2]}); bhi[3 * i + 0] = std::max({xs[0], xs[1], xs[2]});
+        blo[3 * i + 1] = std::min({ys[0], ys[1], ys[2]}); bhi[3 * i + 1] = std::max({ys[0], ys[1], ys[2]});
+        blo[3 * i + 2] = std::min({zs[0], zs[1], zs[2]}); bhi[3 * i + 2] = std::max({zs[0], zs[1], zs[2]});
+        for (int k = 0; k < 3; k++) cen[3 * i + k] = 0.5f * (blo[3 * i + k] + bhi[3 * i + k]);
+    }
+    nodes.clear();
+    nodes.reserve(n + 16);
+    if (n == 0) return;
+    struct Item { int node; size_t b, e; };
+    std::vector<Item> todo;
+    nodes.push_back(RRBuildNode{});
+    todo.push_back({0, 0, n});
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        const size_t cnt = it.e - it.b;
+        Box bb, cb;
+        bb.reset(); cb.reset();
+        for (size_t k = it.b; k < it.e; k++) {
+            const uint32_t p = order[k];
+            bb.grow(&blo[3 * p], &bhi[3 * p]);
+            cb.grow(&cen[3 * p], &cen[3 * p]);
+        }
+        RRBuildNode nd;
+        for (int a = 0; a < 3; a++) { nd.lo[a] = bb.lo[a]; nd.hi[a] = bb.hi[a]; }
+        nd.left = nd.right = -1; nd.first = (int32_t)it.b; nd.count = (int32_t)cnt;
+        size_t mid = it.b;
+        bool split = cnt > 1;
+        if (split) {
+            float best_cost = INFINITY; int best_axis = -1, best_bin = -1;
+            for (int a = 0; a < 3; a++) {
+                const float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.f)) continue;
+                Box bins[NB]; int cnts[NB];
+                for (int b = 0; b < NB; b++) { bins[b].reset(); cnts[b] = 0; }
+                const float k1 = (float)NB * (1.0f - 1e-6f) / ext;
+                for (size_t k = it.b; k < it.e; k++) {
+                    const uint32_t p = order[k];
+                    int b = (int)((cen[3 * p + a] - cb.lo[a]) * k1);
+                    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                    bins[b].grow(&blo[3 * p], &bhi[3 * p]); cnts[b]++;
+                }
+                float right_area[NB]; int right_cnt[NB];
+                Box acc; acc.reset(); int c = 0;
+                for (int b = NB - 1; b >= 1; b--) { acc.grow(bins[b]); c += cnts[b]; right_area[b] = acc.half_area(); right_cnt[b] = c; }
+                acc.reset(); c = 0;
+                for (int b = 1; b < NB; b++) {
+                    acc.grow(bins[b - 1]); c += cnts[b - 1];
+                    if (c == 0 || right_cnt[b] == 0) continue;
+                    const float cost = acc.half_area() * (float)c + right_area[b] * (float)right_cnt[b];
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+                }
+            }
+            if (best_axis >= 0) {
+                const float area = bb.half_area();
+                if (cnt <= (size_t)RR_MAX_LEAF && (float)cnt * area <= 1.0f * area + best_cost) {
+                    split = false;                                   /* leaf is cheaper */
+                } else {
+                    const int a = best_axis;
+                    const float ext = cb.hi[a] - cb.lo[a];
+                    const float k1 = (float)NB * (1.0f - 1e-6f) / ext;
+                    const float clo = cb.lo[a];
+                    auto m = std::partition(order.begin() + it.b, order.begin() + it.e, [&](uint32_t p) {
+                        int b = (int)((cen[3 * p + a] - clo) * k1);
+                        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                        return b < best_bin;
+                    });
+                    mid = (size_t)(m - order.begin());
+                }
+            }
+            if (split && (mid == it.b || mid == it.e)) {             /* degenerate: identical centroids */
+                if (cnt <= (size_t)RR_MAX_LEAF) split = false;
+                else mid = it.b + cnt / 2;
+            }
+        }
+        if (split) {
+            nd.count = 0;
+            nd.left = (int32_t)nodes.size(); nodes.push_back(RRBuildNode{});
+            nd.right = (int32_t)nodes.size(); nodes.push_back(RRBuildNode{});
+            todo.push_back({nd.right, mid, it.e});
+            todo.push_back({nd.left, it.b, mid});
+        }
+        nodes[it.node] = nd;
+    }
+}
+
+void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& bn, const std::vector<uint32_t>& order,
+                 RRPackedBVH& out)
+{
+    const size_t n = order.size();
+    out.nodes.clear();
+    out.tris.resize(3 * n);
+    for (size_t k = 0; k < n; k++) {
+        const uint32_t f = order[k];
+        out.tris[3 * k + 0] = make_float4(soup.v0[f].x, soup.v0[f].y, soup.v0[f].z, rr_u2f(f));
+        out.tris[3 * k + 1] = make_float4(soup.e1[f].x, soup.e1[f].y, soup.e1[f].z, rr_u2f(soup.obj[f]));
+        out.tris[3 * k + 2] = make_float4(soup.e2[f].x, soup.e2[f].y, soup.e2[f].z, 0.f);
+    }
+    out.root_ref = 0;
+    if (bn.empty()) {                       /* empty mesh: one node with two empty children */
+        RRNode nd; memset(&nd, 0, sizeof(nd));
+        for (int c = 0; c < 2; c++) for (int a = 0; a < 3; a++) { nd.q[6 * c + a] = 65535; nd.q[6 * c + 3 + a] = 0; }
+        nd.c0 = nd.c1 = RR_REF_EMPTY;
+        out.nodes.push_back(nd);
+        for (int a = 0; a < 3; a++) { out.grid_origin[a] = 0.f; out.grid_scale[a] = 1.f; }
+        return;
+    }
+    /* grid over the padded scene box */
+    float pad[3];
+    for (int a = 0; a < 3; a++) {
+        const float lo = bn[0].lo[a], hi = bn[0].hi[a];
+        pad[a] = 1e-5f * std::max(1.0f, std::max(std::fabs(lo), std::fabs(hi)));
+        out.grid_origin[a] = lo - 2.f * pad[a];
+        out.grid_scale[a] = ((hi - lo) + 4.f * pad[a]) / 65535.0f;
+    }
+    auto quant = [&](const RRBuildNode& b, uint16_t* q) {
+        for (int a = 0; a < 3; a++) {
+            const float o = out.grid_origin[a], s = out.grid_scale[a];
+            const float lo = b.lo[a] - pad[a], hi = b.hi[a] + pad[a];
+            int ql = (int)std::floor((lo - o) / s), qh = (int)std::ceil((hi - o) / s);
+            ql = std::min(std::max(ql, 0), 65535); qh = std::min(std::max(qh, 0), 65535);
+            while (ql > 0 && fmaf((float)ql, s, o) > lo) ql--;          /* conservative under the decode expression */
+            while (qh < 65535 && fmaf((float)qh, s, o) < hi) qh++;
+            q[a] = (uint16_t)ql; q[3 + a] = (uint16_t)qh;
+        }
+    };
+    auto leaf_ref = [&](const RRBuildNode& b) -> uint32_t {
+        return RR_REF_LEAF | ((uint32_t)(b.count - 1) << 28) | (uint32_t)b.first;
+    };
+    if (bn[0].left < 0) {                   /* single-leaf mesh */
+        RRNode nd; memset(&nd, 0, sizeof(nd));
+        quant(bn[0], &nd.q[0]);
+        for (int a = 0; a < 3; a++) { nd.q[6 + a] = 65535; nd.q[9 + a] = 0; }
+        nd.c0 = leaf_ref(bn[0]); nd.c1 = RR_REF_EMPTY;
+        out.nodes.push_back(nd);
+        return;
+    }
+    /* DFS preorder numbering of inner nodes */
+    std::vector<int32_t> packed_idx(bn.size(), -1);
+    std::vector<int32_t> stack; stack.push_back(0);
+    int32_t next = 0;
+    while (!stack.empty()) {
+        const int32_t i = stack.back(); stack.pop_back();
+        packed_idx[i] = next++;
+        if (bn[bn[i].right].left >= 0) stack.push_back(bn[i].right);
+        if (bn[bn[i].left].left >= 0) stack.push_back(bn[i].left);
+    }
+    out.nodes.resize(next);
+    for (size_t i = 0; i < bn.size(); i++) {
+        if (packed_idx[i] < 0) continue;
+        RRNode nd; memset(&nd, 0, sizeof(nd));
+        const RRBuildNode& L = bn[bn[i].left];
+        const RRBuildNode& R = bn[bn[i].right];
+        quant(L, &nd.q[0]);
+        quant(R, &nd.q[6]);
+        nd.c0 = (L.left >= 0) ? (uint32_t)packed_idx[bn[i].left] : leaf_ref(L);
+        nd.c1 = (R.left >= 0) ? (uint32_t)packed_idx[bn[i].right] : leaf_ref(R);
+        out.nodes[packed_idx[i]] = nd;
+    }
+}

@@ -1,0 +1,26 @@
+/* rr_bvh.h — BVH construction entry points (host side of the library). */
+#ifndef RR_BVH_H
+#define RR_BVH_H
+#include <vector>
+#include "rr_internal.h"
+
+struct RRPackedBVH {
+    std::vector<RRNode> nodes;
+    std::vector<float4> tris;          /* 3 per triangle, leaf order */
+    uint32_t root_ref = 0;
+    float grid_origin[3] = {0, 0, 0}, grid_scale[3] = {1, 1, 1};
+};
+
+/* per-face (v0, e1, e2) as the kernels and the oracle define them: e1 = v1 - v0, e2 = v2 - v0 in fp32 */
+struct RRTriSoup {
+    std::vector<rr_vec3> v0, e1, e2;
+    std::vector<uint32_t> obj;
+};
+
+/* Binned-SAH top-down build on the host (bring-up / fallback for tiny meshes). */
+void rr_bvh_build_host(const RRTriSoup& soup, std::vector<RRBuildNode>& nodes, std::vector<uint32_t>& order);
+
+/* Quantise + reorder: RRBuildNode tree -> 32-byte nodes + leaf-ordered triangles. */
+void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& nodes, const std::vector<uint32_t>& order,
+                 RRPackedBVH& out);
+#endif

@@ -1,0 +1,616 @@
+/* rr_kernels.cu — sm_100a kernels of the RadaRays hot path.
+ *
+ * rr_frame_kernel fuses, per (pose, azimuth) work item owned by one persistent CTA:
+ *   beam bundle generation      (RadarCPU.cpp:184-209, radar_algorithms.cpp:150-169)
+ *   closest-hit traversal       (Rmagine/Embree call at RadarCPU.cpp:236) over the 32-byte quantised BVH
+ *   move + Snell/Fresnel + BRDF (radar_types.h:108-120, radar_algorithms.h:55-139,168-187, RadarCPU.cpp:243-371)
+ *   pruning + ordered respawn   (RadarCPU.cpp:288-290,364-389) via block scans (keeps the reference's list order)
+ *   range-bin accumulation      (RadarCPU.cpp:402-450) into a shared-memory column, in reference order
+ *   energy_max / ambient noise / normalise / mono8 (RadarCPU.cpp:453-542)
+ * The arithmetic is written independently of oracle/rr_oracle.cpp; only the elementary primitives of
+ * rr_detmath.h are shared. Compile with --fmad=false: every fused multiply-add below is explicit.
+ */
+#include "rr_internal.h"
+
+#define RR_WARPS (RR_BLOCK / 32)
+#define RR_FULL 0xffffffffu
+
+/* Wave state. Quirk kept on purpose: the reference never updates DirectedWave::velocity on the waves it pushes
+ * (RadarCPU.cpp:285-286,364-365 copy only dir and energy out of fresnel()'s result), so every wave travels with
+ * the initial 0.3 m/ns (RadarCPU.cpp:110) and only material_id tracks the medium. velocity is therefore a
+ * constant here, not per-wave state. */
+#define RR_WAVE_VELOCITY 0.3
+struct RRWave {
+    rr_vec3 o, d;
+    double energy, time;
+    uint32_t mat;
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * closest hit: smallest t, ties -> lowest face id (rr_detmath.h). Returns triangle SLOT or -1.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ float rr_q16(uint32_t w, int hi) { return (float)(hi ? (w >> 16) : (w & 0xffffu)); }
+
+template <bool STATS>
+__device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const float4* __restrict__ tris,
+                                        uint32_t root_ref, const float* go, const float* gs,
+                                        rr_vec3 o, rr_vec3 d, float tmax, float& t_hit, int& face_hit,
+                                        unsigned& n_nodes, unsigned& n_tris)
+{
+    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    const float gox = go[0], goy = go[1], goz = go[2];
+    const float gsx = gs[0], gsy = gs[1], gsz = gs[2];
+    uint32_t stack[RR_STACK_SIZE];
+    int sp = 0;
+    uint32_t cur = root_ref;
+    float best_t = INFINITY;
+    int best_face = -1, best_slot = -1;
+    float limit = tmax * 1.00001f + 1e-6f;        /* prune slack >> rounding error of t (ties must be visited) */
+
+    while (true) {
+        if (!(cur & RR_REF_LEAF)) {
+            const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
+            const uint4 a = __ldg(np);
+            const uint4 b = __ldg(np + 1);
+            if (STATS) n_nodes++;
+            /* child 0: lo = (a.x.lo, a.x.hi, a.y.lo) hi = (a.y.hi, a.z.lo, a.z.hi) */
+            float t0n, t0f, t1n, t1f;
+            {
+                const float lx = fmaf(rr_q16(a.x, 0), gsx, gox), ly = fmaf(rr_q16(a.x, 1), gsy, goy), lz = fmaf(rr_q16(a.y, 0), gsz, goz);
+                const float hx = fmaf(rr_q16(a.y, 1), gsx, gox), hy = fmaf(rr_q16(a.z, 0), gsy, goy), hz = fmaf(rr_q16(a.z, 1), gsz, goz);
+                const float ax = (lx - o.x) * ix, bx = (hx - o.x) * ix;
+                const float ay = (ly - o.y) * iy, by = (hy - o.y) * iy;
+                const float az = (lz - o.z) * iz, bz = (hz - o.z) * iz;
+                t0n = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+                t0f = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), limit));
+            }
+            {
+                const float lx = fmaf(rr_q16(a.w, 0), gsx, gox), ly = fmaf(rr_q16(a.w, 1), gsy, goy), lz = fmaf(rr_q16(b.x, 0), gsz, goz);
+                const float hx = fmaf(rr_q16(b.x, 1), gsx, gox), hy = fmaf(rr_q16(b.y, 0), gsy, goy), hz = fmaf(rr_q16(b.y, 1), gsz, goz);
+                const float ax = (lx - o.x) * ix, bx = (hx - o.x) * ix;
+                const float ay = (ly - o.y) * iy, by = (hy - o.y) * iy;
+                const float az = (lz - o.z) * iz, bz = (hz - o.z) * iz;
+                t1n = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+                t1f = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), limit));
+            }
+            const bool h0 = (t0n <= t0f * 1.0000005f) && (b.z != RR_REF_EMPTY);
+            const bool h1 = (t1n <= t1f * 1.0000005f) && (b.w != RR_REF_EMPTY);
+            if (h0 && h1) {
+                const bool first0 = t0n <= t1n;
+                cur = first0 ? b.z : b.w;
+                if (sp < RR_STACK_SIZE) stack[sp++] = first0 ? b.w : b.z;
+            } else if (h0) {
+                cur = b.z;
+            } else if (h1) {
+                cur = b.w;
+            } else {
+                if (sp == 0) break;
+                cur = stack[--sp];
+            }
+        } else {
+            const uint32_t first = cur & 0x0fffffffu;
+            const uint32_t cnt = ((cur >> 28) & 7u) + 1u;
+            for (uint32_t k = 0; k < cnt; k++) {
+                const float4 q0 = __ldg(tris + 3 * (first + k));
+                const float4 q1 = __ldg(tris + 3 * (first + k) + 1);
+                const float4 q2 = __ldg(tris + 3 * (first + k) + 2);
+                if (STATS) n_tris++;
+                float t;
+                if (rr_ray_triangle(o, d, rr_v3(q0.x, q0.y, q0.z), rr_v3(q1.x, q1.y, q1.z), rr_v3(q2.x, q2.y, q2.z), tmax, &t)) {
+                    const int face = (int)__float_as_uint(q0.w);
+                    if (best_face < 0 || t < best_t || (t == best_t && face < best_face)) {
+                        best_t = t; best_face = face; best_slot = (int)(first + k);
+                        limit = best_t * 1.00001f + 1e-6f;
+                    }
+                }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    t_hit = best_t;
+    face_hit = best_face;
+    return best_slot;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * block-wide exclusive scan of one 32-bit value per thread (two 16-bit fields are scanned at once)
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t rr_block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t nb = __shfl_up_sync(RR_FULL, incl, off);
+        if (lane >= off) incl += nb;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = (lane < RR_WARPS) ? s_warp[lane] : 0u;
+#pragma unroll
+        for (int off = 1; off < RR_WARPS; off <<= 1) {
+            const uint32_t nb = __shfl_up_sync(RR_FULL, x, off);
+            if (lane >= off) x += nb;
+        }
+        if (lane < RR_WARPS) s_warp[lane] = x;
+    }
+    __syncthreads();
+    const uint32_t prefix = (wid > 0) ? s_warp[wid - 1] : 0u;
+    total = s_warp[RR_WARPS - 1];
+    __syncthreads();
+    return prefix + incl - v;
+}
+
+/* Ken Perlin's reference permutation (image_algorithms.h:14-50 holds it twice back to back) */
+__constant__ unsigned char c_perlin_perm[256] = {
+    151,160,137,91,90,15,131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,190,6,148,
+    247,120,234,75,0,26,197,62,94,252,219,203,117,35,11,32,57,177,33,88,237,149,56,87,174,20,125,136,171,168,68,175,
+    74,165,71,134,139,48,27,166,77,146,158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,244,102,143,54,
+    65,25,63,161,1,216,80,73,209,76,132,187,208,89,18,169,200,196,135,130,116,188,159,86,164,100,109,198,173,186,3,64,
+    52,217,226,250,124,123,5,202,38,147,118,126,255,82,85,212,207,206,59,227,47,16,58,17,182,189,28,42,223,183,170,213,
+    119,248,152,2,44,154,163,70,221,153,101,155,167,43,172,9,129,22,39,253,19,98,108,110,79,113,224,232,178,185,112,104,
+    218,246,97,228,251,34,242,193,238,210,144,12,191,179,162,241,81,51,145,235,249,14,239,107,49,192,214,31,181,199,106,157,
+    184,84,204,176,115,121,50,45,127,4,150,254,138,236,205,93,222,114,67,29,24,72,243,141,128,195,78,66,215,61,156,180};
+
+/* 2-D slice (z = 0) of the improved-noise function, image_algorithms.h:69-106.
+ * With z = 0 the outer blend weight fade(0) is exactly 0, so lerp(w, lower, upper) = lower + 0*(upper-lower)
+ * = lower bit-for-bit (upper is finite); only the z-layer-0 gradients are evaluated here. */
+__device__ __forceinline__ double rr_pgrad(int h, double x, double y)
+{
+    h &= 15;
+    const double u = (h < 8) ? x : y;
+    const double v = (h < 4) ? y : ((h == 12 || h == 14) ? x : 0.0);
+    return ((h & 1) ? -u : u) + ((h & 2) ? -v : v);
+}
+__device__ __forceinline__ double rr_pfade(double t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+__device__ __forceinline__ double rr_plerp(double t, double a, double b) { return a + t * (b - a); }
+__device__ double rr_perlin2(const unsigned char* perm, double sx, double sy)
+{
+    const double fx = floor(sx), fy = floor(sy);
+    const int X = ((int)fx) & 255, Y = ((int)fy) & 255;
+    const double x = sx - fx, y = sy - fy;
+    const double u = rr_pfade(x), v = rr_pfade(y);
+    const int A = perm[X] + Y, B = perm[(X + 1) & 255] + Y;
+    const int AA = perm[A & 255], AB = perm[(A + 1) & 255], BA = perm[B & 255], BB = perm[(B + 1) & 255];
+    const double g00 = rr_pgrad(perm[AA], x, y), g10 = rr_pgrad(perm[BA], x - 1, y);
+    const double g01 = rr_pgrad(perm[AB], x, y - 1), g11 = rr_pgrad(perm[BB], x - 1, y - 1);
+    const double lower = rr_plerp(v, rr_plerp(u, g00, g10), rr_plerp(u, g01, g11));
+    return lower + 0.0 * 0.0;   /* == lerp(0, lower, upper) */
+}
+
+/* (cell) of a return, RadarCPU.cpp:410-413 */
+__device__ __forceinline__ int rr_signal_cell(double time, double resolution)
+{
+    const float half_time = (float)(time / 2.0);
+    const float dist = (float)(0.3 * (double)half_time);
+    const double c = (double)dist / resolution;
+    return (c >= -2147483648.0 && c < 2147483648.0) ? (int)c : INT32_MIN;
+}
+
+/* mono8 conversion of cv::Mat::convertTo(CV_8UC1): cvRound (half to even) + saturate; NaN/overflow -> 0 */
+__device__ __forceinline__ uint8_t rr_to_u8(float v)
+{
+    if (!(fabsf(v) < 2147483648.0f)) return 0;
+    const int r = __float2int_rn(v);
+    return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * the fused frame kernel
+ * ---------------------------------------------------------------------------------------------- */
+template <bool STATS, bool DEBUG>
+__global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams P)
+{
+    extern __shared__ float s_col[];                     /* n_cells floats: this azimuth's range column */
+    __shared__ float s_weights[RR_MAX_DENOISE];
+    __shared__ unsigned char s_perm[256];
+    __shared__ uint32_t s_scan[RR_WARPS];
+    __shared__ float s_red[RR_WARPS];
+    __shared__ uint32_t s_item, s_next_base, s_sig_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? P.denoise_weights[i] : 0.f;
+    for (int i = tid; i < 256; i += RR_BLOCK) s_perm[i] = c_perlin_perm[i];
+
+    const uint32_t cap = P.wave_cap, scap = P.sig_cap;
+    float* wf = P.wave_f32 + (size_t)blockIdx.x * 2 * 6 * cap;
+    double* wd = P.wave_f64 + (size_t)blockIdx.x * 2 * 2 * cap;
+    uint32_t* wm = P.wave_mat + (size_t)blockIdx.x * 2 * cap;
+    int32_t* sg_cell = P.sig_cell + (size_t)blockIdx.x * scap;
+    float* sg_str = P.sig_strength + (size_t)blockIdx.x * scap;
+    const int C = P.n_cells;
+    const uint32_t total_items = (uint32_t)P.n_poses * (uint32_t)P.az_count;
+    const float go[3] = {P.grid_origin[0], P.grid_origin[1], P.grid_origin[2]};
+    const float gs[3] = {P.grid_scale[0], P.grid_scale[1], P.grid_scale[2]};
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(P.work_counter, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= total_items) break;
+        const int pose_i = (int)(item / (uint32_t)P.az_count);
+        const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
+
+        /* Tam = Tsm * Tas (RadarCPU.cpp:201-206); Tas.t = 0 */
+        const rr_pose ps = P.poses[P.pose_per_azimuth ? (pose_i * RR_N_ANGLES + az) : pose_i];
+        rr_quat Rsm; Rsm.x = ps.qx; Rsm.y = ps.qy; Rsm.z = ps.qz; Rsm.w = ps.qw;
+        const float4 tq = P.tas_quat[az];
+        rr_quat Ras; Ras.x = tq.x; Ras.y = tq.y; Ras.z = tq.z; Ras.w = tq.w;
+        const rr_quat R = rr_qmul(Rsm, Ras);
+        const rr_quat Rinv = rr_qinv(R);
+        const rr_vec3 T = rr_add(rr_qrot(Rsm, rr_v3(0.f, 0.f, 0.f)), rr_v3(ps.tx, ps.ty, ps.tz));
+
+        for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
+        if (tid == 0) s_sig_base = 0;
+
+        uint32_t n_cur = (uint32_t)P.n_samples;
+        int cur = 0;
+        uint32_t cast_base = 0;
+        unsigned long long item_hits = 0;
+        unsigned stat_nodes = 0, stat_tris = 0;
+        uint32_t max_waves = n_cur;
+
+        for (int pass = 0; pass < P.n_passes; pass++) {
+            __syncthreads();
+            if (tid == 0) s_next_base = 0;
+            __syncthreads();
+            const float* cf = wf + (size_t)cur * 6 * cap;
+            const double* cd = wd + (size_t)cur * 2 * cap;
+            const uint32_t* cm = wm + (size_t)cur * cap;
+            float* nf = wf + (size_t)(cur ^ 1) * 6 * cap;
+            double* ndp = wd + (size_t)(cur ^ 1) * 2 * cap;
+            uint32_t* nm = wm + (size_t)(cur ^ 1) * cap;
+
+            for (uint32_t base = 0; base < n_cur; base += RR_BLOCK) {
+                const uint32_t i = base + tid;
+                const bool active = i < n_cur;
+                uint32_t n_child = 0, n_sig = 0;
+                /* results to be appended in order */
+                rr_vec3 c_o = rr_v3(0, 0, 0), c_d0 = c_o, c_d1 = c_o;
+                double c_time = 0, c_e0 = 0, c_e1 = 0;
+                uint32_t c_m0 = 0, c_m1 = 0;
+                bool keep0 = false, keep1 = false;
+                int sig_cell0 = 0, sig_cell1 = 0;
+                float sig_s0 = 0, sig_s1 = 0, sig_t0 = 0, sig_t1 = 0;
+                bool hit = false;
+                int face = -1; float range = 0.f; float dbg_energy = 0.f;
+
+                if (active) {
+                    RRWave w;
+                    if (pass == 0) {                      /* RadarCPU.cpp:106-114,184 */
+                        w.o = rr_v3(0.f, 0.f, 0.f);
+                        w.d = rr_v3(P.beam_dirs[3 * i], P.beam_dirs[3 * i + 1], P.beam_dirs[3 * i + 2]);
+                        w.energy = 1.0; w.time = 0.0; w.mat = 0u;
+                    } else {
+                        w.o = rr_v3(cf[0 * cap + i], cf[1 * cap + i], cf[2 * cap + i]);
+                        w.d = rr_v3(cf[3 * cap + i], cf[4 * cap + i], cf[5 * cap + i]);
+                        w.energy = cd[0 * cap + i]; w.time = cd[1 * cap + i];
+                        w.mat = cm[i];
+                    }
+                    dbg_energy = (float)w.energy;
+                    /* ray into the map frame; closest hit within [0, 1000] m (radar_algorithms.cpp:157-158) */
+                    const rr_vec3 o_m = rr_add(rr_qrot(R, w.o), T);
+                    const rr_vec3 d_m = rr_qrot(R, w.d);
+                    const int slot = rr_trace<STATS>(P.nodes, P.tris, P.root_ref, go, gs, o_m, d_m, 1000.0f,
+                                                     range, face, stat_nodes, stat_tris);
+                    if (slot >= 0) {
+                        const float4 q1 = __ldg(P.tris + 3 * slot + 1);
+                        const float4 q2 = __ldg(P.tris + 3 * slot + 2);
+                        const uint32_t obj = __float_as_uint(q1.w);
+                        if (obj >= (uint32_t)P.n_objects) {
+                            atomicExch(&P.error_flags[1], 1);
+                        } else {
+                            hit = true;
+                            /* geometric normal -> ray frame, facing the ray, re-normalised (RadarCPU.cpp:248) */
+                            rr_vec3 n = rr_normalize(rr_cross(rr_v3(q1.x, q1.y, q1.z), rr_v3(q2.x, q2.y, q2.z)));
+                            n = rr_qrot(Rinv, n);
+                            if (rr_dot(w.d, n) > 0.0f) n = rr_neg(n);
+                            n = rr_normalize(n);
+
+                            /* move to the surface (radar_types.h:108-113) */
+                            const rr_vec3 p_hit = rr_add(w.o, rr_muls(w.d, range));
+                            const double wave_v = RR_WAVE_VELOCITY;
+                            const double t_hit = w.time + (double)range / wave_v;
+
+                            /* medium on the far side (RadarCPU.cpp:266-280) */
+                            const uint32_t air = (uint32_t)P.material_id_air;
+                            const uint32_t mat_t = (w.mat == air) ? (uint32_t)P.object_materials[obj] : air;
+                            const float4 mt = P.materials[mat_t];
+                            const float v_t = (w.mat != mat_t) ? mt.x : (float)wave_v;
+
+                            /* Snell/Fresnel (radar_algorithms.h:55-139): n1 := v2, n2 := v1 */
+                            const double n1 = (double)v_t, n2 = wave_v;
+                            const float cos_i = rr_dot(rr_neg(w.d), n);
+                            const double th_i = (double)rr_acosf(cos_i);
+                            const rr_vec3 d_refl = rr_add(w.d, rr_muls(rr_muls(n, 2.0f), rr_dot(rr_neg(n), w.d)));
+                            rr_vec3 d_refr = rr_v3(0.f, 0.f, 0.f);
+                            rr_vec3 nn = n;
+                            if (n1 > 0.0) {
+                                const double n21 = n2 / n1;
+                                double th_limit = 100.0;
+                                if (fabs(n21) <= 1.0) th_limit = rr_asin(n21);
+                                if (th_i <= th_limit) {
+                                    if (rr_dot(nn, w.d) > 0.0f) nn = rr_neg(nn);
+                                    if (n2 > 0.0) {
+                                        const double n12 = n1 / n2;
+                                        const double c = rr_cos(th_i);
+                                        const double k = n12 * c - sqrt(1 - n12 * n12 * (1 - c * c));
+                                        d_refr = rr_add(rr_muls(w.d, (float)n12), rr_muls(nn, (float)k));
+                                    }
+                                }
+                            }
+                            const double th_t = (double)rr_acosf(rr_dot(d_refr, rr_neg(nn)));
+                            double rs, rp;
+                            const double th_sum = th_i + th_t;
+                            if (th_sum < 0.0001) {
+                                rs = (n1 - n2) / (n1 + n2); rp = rs;
+                            } else if (th_sum > M_PI - 0.0001) {
+                                rs = 1.0; rp = 1.0;
+                            } else {
+                                const double th_dif = th_i - th_t;
+                                rs = -rr_sin(th_dif) / rr_sin(th_sum);
+                                rp = rr_tan(th_dif) / rr_tan(th_sum);
+                            }
+                            const double Reff = 0.5 * (rs * rs) + (1.0 - 0.5) * (rp * rp);
+                            const double Teff = 1.0 - Reff;
+                            const double e_refl = Reff * w.energy;
+                            const double e_refr = Teff * w.energy;
+                            const double thr = (double)0.001f;                 /* Radar.cpp:24 */
+
+                            c_o = p_hit; c_time = t_hit;
+                            if (e_refl > thr) {                                /* RadarCPU.cpp:288 */
+                                keep0 = true; c_d0 = d_refl; c_e0 = e_refl; c_m0 = w.mat;
+                                if (w.mat == air) {                            /* :302 — return to the sensor */
+                                    const float th_if = (float)(double)rr_acosf(rr_dot(rr_neg(w.d), n));
+                                    const float e_f = (float)e_refl;
+                                    {   /* BRDF, radar_algorithms.h:168-187: (A, B, C) = (ambient, diffuse, specular) */
+                                        const float lobe = rr_powf(rr_cosf(th_if), mt.w);
+                                        const float total = mt.y * 1.0f + mt.z * lobe;
+                                        const float ret = total * e_f;
+                                        if (pass == 0 || P.record_multi_reflection) {
+                                            const float t_back = (float)(t_hit * 2.0);
+                                            sig_cell0 = rr_signal_cell((double)t_back, P.resolution);
+                                            sig_s0 = ret; sig_t0 = t_back; n_sig = 1;
+                                        }
+                                    }
+                                    if (pass > 0 && P.record_multi_path) {     /* :325-360 */
+                                        const float dist_f = rr_l2norm(p_hit);
+                                        const rr_vec3 to_hit = rr_divs(p_hit, rr_l2norm(p_hit));
+                                        const double t_sensor = (double)dist_f / wave_v;
+                                        const double view = (double)rr_dot(w.d, to_hit);
+                                        const float ang = rr_acosf(rr_dot(rr_neg(d_refl), to_hit));
+                                        if (view > P.multipath_threshold) {
+                                            const float lobe = rr_powf(rr_cosf(ang), mt.w);
+                                            const float total = mt.y * 1.0f + mt.z * lobe;
+                                            const float ret = total * e_f;
+                                            const double t_air = t_hit + t_sensor;
+                                            const int cell = rr_signal_cell(t_air, P.resolution);
+                                            if (n_sig == 0) { sig_cell0 = cell; sig_s0 = ret; sig_t0 = (float)t_air; }
+                                            else { sig_cell1 = cell; sig_s1 = ret; sig_t1 = (float)t_air; }
+                                            n_sig++;
+                                        }
+                                    }
+                                }
+                            }
+                            if (e_refr > thr) {                                /* :364-370 */
+                                keep1 = true; c_d1 = d_refr; c_e1 = e_refr; c_m1 = mat_t;
+                            }
+                            n_child = (keep0 ? 1u : 0u) + (keep1 ? 1u : 0u);
+                        }
+                    }
+                }
+
+                item_hits += (unsigned long long)__syncthreads_count(hit ? 1 : 0);
+                uint32_t tot;
+                const uint32_t excl = rr_block_excl_scan(n_child | (n_sig << 16), s_scan, tot);
+                const uint32_t nb = s_next_base, sb = s_sig_base;
+                uint32_t co = nb + (excl & 0xffffu);
+                const uint32_t so = sb + (excl >> 16);
+                const float skip = 0.001f;                                     /* RadarCPU.cpp:374-378 */
+                if (keep0) {
+                    if (co < cap) {
+                        const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d0, skip));
+                        nf[0 * cap + co] = o2.x; nf[1 * cap + co] = o2.y; nf[2 * cap + co] = o2.z;
+                        nf[3 * cap + co] = c_d0.x; nf[4 * cap + co] = c_d0.y; nf[5 * cap + co] = c_d0.z;
+                        ndp[0 * cap + co] = c_e0; ndp[1 * cap + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
+                        nm[co] = c_m0;
+                    }
+                    co++;
+                }
+                if (keep1) {
+                    if (co < cap) {
+                        const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d1, skip));
+                        nf[0 * cap + co] = o2.x; nf[1 * cap + co] = o2.y; nf[2 * cap + co] = o2.z;
+                        nf[3 * cap + co] = c_d1.x; nf[4 * cap + co] = c_d1.y; nf[5 * cap + co] = c_d1.z;
+                        ndp[0 * cap + co] = c_e1; ndp[1 * cap + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
+                        nm[co] = c_m1;
+                    }
+                }
+                if (n_sig > 0) {
+                    if (so < scap) { sg_cell[so] = sig_cell0; sg_str[so] = sig_s0; }
+                    if (n_sig > 1 && so + 1 < scap) { sg_cell[so + 1] = sig_cell1; sg_str[so + 1] = sig_s1; }
+                    if (DEBUG) {
+                        if (so < P.dbg_sig_cap) {
+                            rr_signal_record r; r.azimuth = az; r.cell = sig_cell0; r.strength = sig_s0; r.time = sig_t0;
+                            P.dbg_signals[(size_t)az * P.dbg_sig_cap + so] = r;
+                        }
+                        if (n_sig > 1 && so + 1 < P.dbg_sig_cap) {
+                            rr_signal_record r; r.azimuth = az; r.cell = sig_cell1; r.strength = sig_s1; r.time = sig_t1;
+                            P.dbg_signals[(size_t)az * P.dbg_sig_cap + so + 1] = r;
+                        }
+                    }
+                }
+                if (DEBUG && active && cast_base + i < P.dbg_cast_cap) {
+                    rr_cast_record r; r.azimuth = az; r.pass = pass; r.face_id = hit ? face : -1;
+                    r.range = hit ? range : 0.f; r.energy = dbg_energy; r.n_children = (int)n_child;
+                    P.dbg_casts[(size_t)az * P.dbg_cast_cap + cast_base + i] = r;
+                }
+                __syncthreads();
+                if (tid == 0) { s_next_base = nb + (tot & 0xffffu); s_sig_base = sb + (tot >> 16); }
+                __syncthreads();
+            }
+            cast_base += n_cur;
+            const uint32_t produced = s_next_base;
+            if (produced > cap && tid == 0) atomicExch(&P.error_flags[0], 1);
+            n_cur = produced < cap ? produced : cap;
+            if (n_cur > max_waves) max_waves = n_cur;
+            cur ^= 1;
+        }
+        __syncthreads();
+        uint32_t n_sigs = s_sig_base;
+        if (n_sigs > scap) { if (tid == 0) atomicExch(&P.error_flags[0], 1); n_sigs = scap; }
+        if (DEBUG && tid == 0) { P.dbg_counts[2 * az] = cast_base; P.dbg_counts[2 * az + 1] = n_sigs; }
+        __threadfence_block();
+
+        /* ---- signals -> column, RadarCPU.cpp:402-450. Bins are partitioned over the warps; every warp walks
+         * the signal list in the reference's order, so each bin sees its additions in exactly that order. */
+        float m = 0.0f;
+        {
+            const int chunk = (C + RR_WARPS - 1) / RR_WARPS;
+            const int b0 = wid * chunk, b1 = min(C, b0 + chunk);
+            const int W = P.denoise_width, mode = P.denoise_mode;
+            for (uint32_t s = 0; s < n_sigs; s++) {
+                const int cell = sg_cell[s];
+                if (!(cell < C)) continue;
+                const float str = sg_str[s];
+                if (P.denoise_on) {
+                    if (cell < -RR_MAX_DENOISE) continue;
+                    const int start = cell - mode;
+                    const int lo = max(start, max(b0, 1));                     /* glob_id > 0, :424 */
+                    const int hi = min(start + W, b1);
+                    if (lo >= hi) continue;
+                    for (int g = lo + lane; g < hi; g += 32) {
+                        const float v = (float)((double)s_col[g] + (double)str * (double)s_weights[g - start]);
+                        s_col[g] = v;
+                        if (v > m) m = v;
+                    }
+                    __syncwarp();
+                } else {
+                    if (cell >= b0 && cell < b1 && cell >= 0) {
+                        if (lane == 0) {
+                            const float old = s_col[cell];
+                            const float v = (old < str) ? str : old;           /* std::max(old, strength) */
+                            s_col[cell] = v;
+                            if (v > m) m = v;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { const float o2 = __shfl_xor_sync(RR_FULL, m, off); if (o2 > m) m = o2; }
+        if (lane == 0) s_red[wid] = m;
+        __syncthreads();
+        float max_val = 0.0f;
+#pragma unroll
+        for (int k = 0; k < RR_WARPS; k++) if (s_red[k] > max_val) max_val = s_red[k];
+
+        /* ---- energy_max, ambient noise, normalise, mono8 (RadarCPU.cpp:453-542) */
+        const int col = (P.scroll_image + az) % RR_N_ANGLES;
+        const uint64_t frame_id = P.frame_id0 + (uint64_t)pose_i;
+        const float signal_amp = max_val - 0.0f;
+        const float noise_at_0 = (float)((double)signal_amp * P.noise_at_signal_0);
+        const float noise_at_1 = (float)((double)signal_amp * P.noise_at_signal_1);
+        const float ne_max = (float)((double)max_val * P.noise_energy_max);
+        const float ne_min = (float)((double)max_val * P.noise_energy_min);
+        const float e_loss = (float)P.noise_energy_loss;
+        const double random_begin = (P.ambient_noise == 2)
+            ? (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 0u) * 1000.0 : 0.0;
+        const float out_scale = (float)(P.signal_max / (double)max_val);
+        const double ycoord1 = (double)col * 0.05, ycoord2 = (double)col * 0.2;
+        uint8_t* out = P.column_major
+            ? P.out + ((size_t)pose_i * P.az_count + (size_t)(az - P.az_begin)) * (size_t)C
+            : P.out + (size_t)pose_i * (size_t)C * RR_N_ANGLES + col;
+        for (int i = tid; i < C; i += RR_BLOCK) {
+            float v = s_col[i] * P.energy_max_f;
+            if (P.ambient_noise) {
+                double p = 0.0;
+                if (P.ambient_noise == 1) {
+                    p = (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 1u + (uint32_t)i);
+                } else if (P.ambient_noise == 2) {
+                    const double p1 = rr_perlin2(s_perm, random_begin + (double)i * 0.05, ycoord1);
+                    const double p2 = rr_perlin2(s_perm, random_begin + (double)i * 0.2, ycoord2);
+                    p = 0.9 * p1 + 0.1 * p2;
+                }
+                const float sn = (float)(1.0 - (double)((v - 0.0f) / signal_amp));
+                const float sn4 = (float)rr_pow4(sn);
+                const float amp = (float)((double)(sn4 * noise_at_0) + (1.0 - (double)sn4) * (double)noise_at_1);
+                float y = (float)((double)amp * p);
+                const float x = (float)(((double)(float)i + 0.5) * P.resolution);
+                y = y + (ne_max - ne_min) * rr_expf(-e_loss * x) + ne_min;
+                y = fabsf(y);
+                v = v + y;
+            }
+            v = v * out_scale;
+            if (DEBUG && P.dbg_columns) P.dbg_columns[(size_t)az * C + i] = v;
+            const uint8_t px = rr_to_u8(v);
+            if (P.column_major) out[i] = px; else out[(size_t)i * RR_N_ANGLES] = px;
+        }
+
+        /* ---- counters */
+        if (STATS) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                stat_nodes += __shfl_xor_sync(RR_FULL, stat_nodes, off);
+                stat_tris += __shfl_xor_sync(RR_FULL, stat_tris, off);
+            }
+            if (lane == 0) {
+                atomicAdd(&P.counters[3], (unsigned long long)stat_nodes);
+                atomicAdd(&P.counters[4], (unsigned long long)stat_tris);
+            }
+        }
+        if (tid == 0) {
+            atomicAdd(&P.counters[0], (unsigned long long)cast_base);
+            atomicAdd(&P.counters[1], item_hits);
+            atomicAdd(&P.counters[2], (unsigned long long)n_sigs);
+            atomicMax(&P.counters[5], (unsigned long long)max_waves);
+        }
+    }
+}
+
+/* raw closest-hit probe (rr_cast_rays) */
+__global__ void rr_cast_kernel(const RRNode* nodes, const float4* tris, uint32_t root_ref,
+                               float gox, float goy, float goz, float gsx, float gsy, float gsz,
+                               const float* origins, const float* dirs, size_t n, float tmax,
+                               int32_t* face_ids, float* ranges)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float go[3] = {gox, goy, goz}, gs[3] = {gsx, gsy, gsz};
+    unsigned a = 0, b = 0;
+    float t; int face;
+    rr_trace<false>(nodes, tris, root_ref, go, gs, rr_v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
+                    rr_v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmax, t, face, a, b);
+    face_ids[i] = face;
+    ranges[i] = t;
+}
+
+/* ---- host-side launchers (called from rr_api.cu) ------------------------------------------------*/
+extern "C" cudaError_t rr_launch_frame(const RRFrameParams* P, int grid, size_t smem, cudaStream_t st, int stats, int debug)
+{
+    if (debug) rr_frame_kernel<true, true><<<grid, RR_BLOCK, smem, st>>>(*P);
+    else if (stats) rr_frame_kernel<true, false><<<grid, RR_BLOCK, smem, st>>>(*P);
+    else rr_frame_kernel<false, false><<<grid, RR_BLOCK, smem, st>>>(*P);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t rr_frame_occupancy(int* blocks_per_sm, size_t smem)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rr_frame_kernel<false, false>, RR_BLOCK, smem);
+}
+
+extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
+                                      const float* gs, const float* origins, const float* dirs, size_t n, float tmax,
+                                      int32_t* face_ids, float* ranges, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const int block = 128;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    rr_cast_kernel<<<grid, block, 0, st>>>(nodes, tris, root_ref, go[0], go[1], go[2], gs[0], gs[1], gs[2],
+                                           origins, dirs, n, tmax, face_ids, ranges);
+    return cudaGetLastError();
+}

@@ -1,0 +1,183 @@
+"""RadarB200 — host-side mirror of the reference's simulator interface for the hot path.
+
+Mirrors `class Radar` / `RadarCPU` (include/radarays_ros/Radar.hpp:34-107, RadarCPU.hpp:17-36):
+  simulate(...)            <- Radar::simulate(ros::Time), returns the mono8 polar image (n_cells x 400) or None
+  getParams / setParams    <- Radar.hpp:51-59
+  updateDynCfg(cfg)        <- Radar::updateDynCfg (Radar.cpp:188-218)
+  loadParams(...)          <- Radar::loadParams   (Radar.cpp:220-226): materials, object_materials, material_id_air
+The ROS-only parts (tf2 lookup, image_transport) stay in the ROS adapter: the pose `Tsm`
+is passed in; `None` pose == "TF unavailable" -> returns None exactly like RadarCPU.cpp:129-133.
+All compute goes through the C ABI (libradarays_b200.so); there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .types import CastRecord, N_ANGLES, Pose, RadarMaterial, RadarModelConfig, SignalRecord, Stats
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RadarB200:
+    def __init__(self, scene=None, cfg=None, device=0, beam_seed=0, noise_seed=0):
+        self._lib = capi.lib()
+        self._ctx = C.c_void_p()
+        capi.check(None, self._lib.rr_create(C.byref(self._ctx), device))
+        self.device = device
+        self.m_cfg = RadarModelConfig()
+        self._lib.rr_config_defaults(C.byref(self.m_cfg))
+        self.m_params_model = None
+        self.has_last = False
+        self.Tsm_last = None
+        self.frame_counter = 0
+        self._beam_seed = beam_seed
+        capi.check(self._ctx, self._lib.rr_set_beam_samples(self._ctx, None, 0, beam_seed))
+        capi.check(self._ctx, self._lib.rr_set_noise_seed(self._ctx, noise_seed))
+        if scene is not None:
+            self.setMap(scene.verts, scene.tris, scene.tri_object)
+            self.loadParams(scene.materials, scene.object_materials, scene.material_id_air)
+        if cfg is not None:
+            self.updateDynCfg(cfg)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rr_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- map / params ------------------------------------------------------------------------------------------
+    def setMap(self, verts, tris, tri_object=None):
+        """rm::import_embree_map + RadarCPU ctor's `map` argument (radar_simulator.cpp:149-158)."""
+        v = np.ascontiguousarray(verts, np.float32)
+        t = np.ascontiguousarray(tris, np.uint32)
+        o = None if tri_object is None else np.ascontiguousarray(tri_object, np.uint32)
+        capi.check(self._ctx, self._lib.rr_set_mesh(self._ctx, _ptr(v), v.shape[0], _ptr(t), t.shape[0], _ptr(o)))
+
+    def loadParams(self, materials, object_materials, material_id_air=0):
+        arr = (RadarMaterial * len(materials))()
+        for i, m in enumerate(materials):
+            if isinstance(m, RadarMaterial):
+                arr[i] = m
+            else:
+                arr[i].velocity, arr[i].ambient, arr[i].diffuse, arr[i].specular = m
+        om = np.ascontiguousarray(object_materials, np.int32)
+        capi.check(self._ctx, self._lib.rr_set_materials(self._ctx, arr, len(materials), _ptr(om), om.size, material_id_air))
+
+    def updateDynCfg(self, cfg, model=None):
+        self.m_cfg = cfg.copy()
+        self.m_params_model = model
+        mp = C.byref(model) if model is not None else None
+        capi.check(self._ctx, self._lib.rr_set_params(self._ctx, mp, C.byref(self.m_cfg)))
+
+    def getParams(self):
+        return self.m_params_model or self.m_cfg.derive_model()
+
+    def setParams(self, model):
+        self.updateDynCfg(self.m_cfg, model)
+
+    def setBeamSamples(self, dirs=None, seed=None):
+        if seed is not None:
+            self._beam_seed = seed
+        d = None if dirs is None else np.ascontiguousarray(dirs, np.float32)
+        capi.check(self._ctx, self._lib.rr_set_beam_samples(self._ctx, _ptr(d), 0 if d is None else d.shape[0], self._beam_seed))
+
+    def getBeamSamples(self):
+        n = C.c_size_t(0)
+        capi.check(self._ctx, self._lib.rr_get_beam_samples(self._ctx, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 3), np.float32)
+        capi.check(self._ctx, self._lib.rr_get_beam_samples(self._ctx, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def setNoiseSeed(self, seed):
+        capi.check(self._ctx, self._lib.rr_set_noise_seed(self._ctx, seed))
+
+    def setMaxWavesPerAzimuth(self, n):
+        capi.check(self._ctx, self._lib.rr_set_max_waves_per_azimuth(self._ctx, n))
+
+    # ---- the hot path --------------------------------------------------------------------------------------------
+    @staticmethod
+    def _poses(poses):
+        if isinstance(poses, Pose):
+            arr = (Pose * 1)()
+            arr[0] = poses
+            return arr
+        if isinstance(poses, C.Array):
+            return poses
+        arr = (Pose * len(poses))()
+        for i, p in enumerate(poses):
+            arr[i] = p if isinstance(p, Pose) else Pose.from_xyz_yaw(*p)
+        return arr
+
+    def simulate(self, Tsm, frame_id=None, return_stats=False):
+        """One frame (Pose), a batch (sequence of Pose) or, with cfg.include_motion, 400 poses per frame.
+        Returns uint8 (n_cells, 400) / (n, n_cells, 400); None when Tsm is None (RadarCPU.cpp:129-133)."""
+        if Tsm is None:
+            if not self.has_last:
+                return None
+            Tsm = self.Tsm_last
+        single = isinstance(Tsm, Pose)
+        arr = self._poses(Tsm)
+        motion = bool(self.m_cfg.include_motion) and len(arr) % N_ANGLES == 0 and len(arr) >= N_ANGLES
+        n = len(arr) // N_ANGLES if motion else len(arr)
+        if frame_id is None:
+            frame_id = self.frame_counter
+        self.frame_counter = frame_id + n
+        out = np.empty((n, self.m_cfg.n_cells, N_ANGLES), np.uint8)
+        st = Stats()
+        fn = self._lib.rr_simulate_motion if motion else self._lib.rr_simulate
+        capi.check(self._ctx, fn(self._ctx, arr, n, frame_id, _ptr(out), C.byref(st)))
+        self.Tsm_last, self.has_last = (Tsm if single else arr[len(arr) - 1]), True
+        img = out[0] if (single or (motion and n == 1)) else out
+        return (img, st) if return_stats else img
+
+    def simulate_stats(self, Tsm, frame_id=0):
+        arr = self._poses(Tsm)
+        out = np.empty((self.m_cfg.n_cells, N_ANGLES), np.uint8)
+        st = Stats()
+        capi.check(self._ctx, self._lib.rr_simulate_stats(self._ctx, arr, frame_id, _ptr(out), C.byref(st)))
+        return out, st
+
+    def simulate_device(self, d_poses_ptr, n_poses, d_out_ptr, frame_id=0, azimuth_begin=0, azimuth_count=N_ANGLES,
+                        column_major=False, pose_per_azimuth=False, stream=0):
+        """Device-resident variant: raw device pointers (ints), enqueued on `stream`, not synchronised."""
+        capi.check(self._ctx, self._lib.rr_simulate_device(
+            self._ctx, C.c_void_p(d_poses_ptr), n_poses, frame_id, azimuth_begin, azimuth_count,
+            1 if column_major else 0, 1 if pose_per_azimuth else 0, C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+    def get_stats(self):
+        st = Stats()
+        capi.check(self._ctx, self._lib.rr_get_stats(self._ctx, C.byref(st)))
+        return st
+
+    # ---- parity probes -------------------------------------------------------------------------------------------
+    def debug_trace(self, Tsm, frame_id=0, capacity=None):
+        arr = self._poses(Tsm)
+        model = self.getParams()
+        cap = capacity or int(N_ANGLES * model.n_samples * (2 ** min(model.n_reflections, 6)))
+        casts = (CastRecord * cap)()
+        sigs = (SignalRecord * (2 * cap))()
+        nc, ns = C.c_size_t(0), C.c_size_t(0)
+        cols = np.zeros((N_ANGLES, self.m_cfg.n_cells), np.float32)
+        img = np.zeros((self.m_cfg.n_cells, N_ANGLES), np.uint8)
+        capi.check(self._ctx, self._lib.rr_debug_trace(self._ctx, arr, frame_id, casts, cap, C.byref(nc), sigs, 2 * cap,
+                                                       C.byref(ns), _ptr(cols), _ptr(img)))
+        assert nc.value <= cap and ns.value <= 2 * cap, "debug_trace capacity too small"
+        return {"image": img, "columns": cols,
+                "casts": np.frombuffer(casts, dtype=np.dtype(CastRecord), count=nc.value).copy(),
+                "signals": np.frombuffer(sigs, dtype=np.dtype(SignalRecord), count=ns.value).copy()}
+
+    def cast_rays(self, origins, dirs, tmax=1000.0):
+        o = np.ascontiguousarray(origins, np.float32)
+        d = np.ascontiguousarray(dirs, np.float32)
+        faces = np.empty(o.shape[0], np.int32)
+        ranges = np.empty(o.shape[0], np.float32)
+        capi.check(self._ctx, self._lib.rr_cast_rays(self._ctx, _ptr(o), _ptr(d), o.shape[0], tmax, _ptr(faces), _ptr(ranges)))
+        return faces, ranges
