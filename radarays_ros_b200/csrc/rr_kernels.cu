@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
             double* ndp = wd + (size_t)(cur ^ 1) * 2 * cap;
             uint32_t* nm = wm + (size_t)(cur ^ 1) * cap;
 
+            const bool last_pass = (pass == P.n_passes - 1);
             for (uint32_t base = 0; base < n_cur; base += RR_BLOCK) {
                 const uint32_t i = base + tid;
                 const bool active = i < n_cur;
@@ -404,8 +405,11 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
                 }
 
                 item_hits += (unsigned long long)__syncthreads_count(hit ? 1 : 0);
+                /* the reference also builds waves_new in its last pass and then drops it (RadarCPU.cpp:380-389);
+                 * nothing traces those waves, so the last pass appends none (n_children is still reported). */
+                if (last_pass) { keep0 = false; keep1 = false; }
                 uint32_t tot;
-                const uint32_t excl = rr_block_excl_scan(n_child | (n_sig << 16), s_scan, tot);
+                const uint32_t excl = rr_block_excl_scan((last_pass ? 0u : n_child) | (n_sig << 16), s_scan, tot);
                 const uint32_t nb = s_next_base, sb = s_sig_base;
                 uint32_t co = nb + (excl & 0xffffu);
                 const uint32_t so = sb + (excl >> 16);

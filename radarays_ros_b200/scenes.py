@@ -135,7 +135,7 @@ def _ground_height(x, y):
             + 0.03 * np.sin(x * 0.9) * np.cos(y * 1.1))
 
 
-def urban(extent=2000.0, ground_n=1400, block=50.0, street=14.0, facade_cell=2.0, seed=SEED, n_poses=16,
+def urban(extent=2000.0, ground_n=1400, block=50.0, street=14.0, facade_cell=3.5, seed=SEED, n_poses=16,
           max_height=30.0, name=None):
     """ground_n x ground_n displaced grid (2*ground_n^2 tris) + extruded buildings with tessellated facades.
     Defaults give ~3.92 M ground + ~1.2 M building triangles (>= 5 M, BASELINE.json configs[1])."""
@@ -243,7 +243,7 @@ WAREHOUSE_MATERIALS = [
 ]
 
 
-def warehouse(cell=0.085, seed=SEED, n_poses=16, name="warehouse-1M"):
+def warehouse(cell=0.165, seed=SEED, n_poses=16, name="warehouse-1M"):
     """60 x 40 x 8 m hall, 20 shelf rows with metal uprights, wood boards, wrapped pallets, glass panes."""
     rng = np.random.default_rng(seed)
     mb = _MeshBuilder()
