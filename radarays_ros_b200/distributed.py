@@ -1,0 +1,76 @@
+"""Multi-GPU sharding of the hot path: one process per GPU (torch.distributed), mesh/BVH replicated.
+
+The path shards without any data-path reduction: every azimuth column has its own rays, its own
+return list and its own max_val normalisation (RadarCPU.cpp:156-548), and Perlin noise depends only on
+(cell, column, random_begin).
+  * pose sharding  (trajectory batches, BASELINE config 5): pose p -> rank p % world; no collective.
+  * azimuth sharding of ONE frame (config 4): rank r renders columns [begin, begin+count) into a column-major
+    shard [count][n_cells] (contiguous), one all_gather of uint8 columns (400 x n_cells bytes in total) over
+    NCCL/NVLink, then a transpose into the reference's row-major n_cells x 400 image with `scroll_image` applied.
+The collective is torch.distributed (NCCL on GPUs, gloo in the CPU tests of this host logic).
+"""
+import numpy as np
+
+from .types import N_ANGLES
+
+
+def azimuth_shard(rank, world, n_angles=N_ANGLES):
+    """Contiguous, balanced split of the azimuths: the first (n_angles % world) ranks get one extra column."""
+    base, extra = divmod(n_angles, world)
+    begin = rank * base + min(rank, extra)
+    count = base + (1 if rank < extra else 0)
+    return begin, count
+
+
+def pose_shard(n_poses, rank, world):
+    """Indices of the poses rank `rank` renders (round-robin: neighbouring trajectory poses cost about the same)."""
+    return list(range(rank, n_poses, world))
+
+
+def assemble_columns(shards, n_cells, scroll_image=0, n_angles=N_ANGLES):
+    """shards: list over ranks of uint8 arrays [count_r][n_cells] (column-major shards, rank order).
+    Returns the reference layout: uint8 [n_cells][n_angles] with column (scroll + azimuth) % n_angles
+    (RadarCPU.cpp:457,542)."""
+    cols = np.concatenate([np.asarray(s, dtype=np.uint8).reshape(-1, n_cells) for s in shards], axis=0)
+    assert cols.shape[0] == n_angles, "shards do not cover all azimuths"
+    img = np.empty((n_cells, n_angles), np.uint8)
+    dst = (scroll_image + np.arange(n_angles)) % n_angles
+    img[:, dst] = cols.T
+    return img
+
+
+def gather_frame(local_columns, rank, world, n_cells, scroll_image=0, group=None):
+    """all_gather of the per-rank column shards (torch uint8 tensors [count_r, n_cells], on the device the process
+    group works on) and assembly of the full frame on every rank. Shards may differ by one column, so every rank
+    pads to the largest shard before the collective."""
+    import torch
+    import torch.distributed as dist
+    counts = [azimuth_shard(r, world)[1] for r in range(world)]
+    cmax = max(counts)
+    buf = torch.zeros((cmax, n_cells), dtype=torch.uint8, device=local_columns.device)
+    buf[: local_columns.shape[0]] = local_columns
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    shards = [out[r][: counts[r]].cpu().numpy() for r in range(world)]
+    return assemble_columns(shards, n_cells, scroll_image)
+
+
+class ShardedRadar:
+    """Azimuth-sharded rendering of single frames on `world` GPUs (one process each)."""
+
+    def __init__(self, radar, rank, world, group=None):
+        self.radar, self.rank, self.world, self.group = radar, rank, world, group
+        self.begin, self.count = azimuth_shard(rank, world)
+
+    def simulate(self, pose, frame_id=0):
+        import torch
+        dev = torch.device("cuda", self.radar.device)
+        cfg = self.radar.m_cfg
+        p = np.frombuffer(self.radar._poses(pose), dtype=np.float32).reshape(-1, 7).copy()
+        d_pose = torch.from_numpy(p).to(dev)
+        d_cols = torch.empty((self.count, cfg.n_cells), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        self.radar.simulate_device(d_pose.data_ptr(), 1, d_cols.data_ptr(), frame_id=frame_id,
+                                   azimuth_begin=self.begin, azimuth_count=self.count, column_major=True,
+                                   stream=stream.cuda_stream)
+        return gather_frame(d_cols, self.rank, self.world, cfg.n_cells, cfg.scroll_image, self.group)
