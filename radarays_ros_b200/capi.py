@@ -6,7 +6,7 @@ import os
 from .types import RadarModel, RadarModelConfig, Stats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libradarays_b200.so")
+LIB_PATH = os.environ.get("RADARAYS_B200_LIB", os.path.join(_HERE, "libradarays_b200.so"))   # override: tuning builds
 _LIB = None
 
 SYMBOLS = [

@@ -456,24 +456,24 @@ static int ensure_scratch(rr_ctx* ctx)
     if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "frame kernel does not fit on an SM (smem %zu)", smem);
     const int grid = ctx->num_sms * per_sm;
     const uint32_t S = ctx->model.n_samples, Pn = ctx->model.n_reflections;
-    uint32_t cap = ctx->max_waves_user;
-    if (cap == 0) {   /* default: room for 3 dielectric splits per sample path */
-        const uint32_t growth = 1u << std::min<uint32_t>(Pn > 0 ? Pn - 1 : 0, 3);
-        cap = S * growth;
-    }
-    cap = std::max<uint32_t>(cap, S);
-    cap = (cap + 31u) & ~31u;
-    const uint32_t scap = 2u * cap * std::max<uint32_t>(1, std::min<uint32_t>(Pn, 4));
-    if (grid != ctx->grid || cap != ctx->wave_cap || scap != ctx->sig_cap) {
+    const uint32_t spw = (S + RR_WARPS - 1) / RR_WARPS;              /* samples per warp */
+    uint32_t cap_w;
+    if (ctx->max_waves_user) cap_w = (ctx->max_waves_user + RR_WARPS - 1) / RR_WARPS;
+    else cap_w = spw * (1u << std::min<uint32_t>(Pn > 0 ? Pn - 1 : 0, 3));   /* room for 3 dielectric splits per path */
+    cap_w = std::max<uint32_t>(cap_w, spw);
+    cap_w = (cap_w + 31u) & ~31u;
+    const uint32_t scap_w = 2u * cap_w * std::max<uint32_t>(1, std::min<uint32_t>(Pn, 6));
+    if (grid != ctx->grid || cap_w != ctx->wave_cap || scap_w != ctx->sig_cap) {
         cudaFree(ctx->d_wave_f32); cudaFree(ctx->d_wave_f64); cudaFree(ctx->d_wave_mat); cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str);
         ctx->d_wave_f32 = nullptr; ctx->d_wave_f64 = nullptr; ctx->d_wave_mat = nullptr; ctx->d_sig_cell = nullptr; ctx->d_sig_str = nullptr;
         ctx->grid = 0;
-        CK(cudaMalloc((void**)&ctx->d_wave_f32, (size_t)grid * 2 * 6 * cap * sizeof(float)));
-        CK(cudaMalloc((void**)&ctx->d_wave_f64, (size_t)grid * 2 * 2 * cap * sizeof(double)));
-        CK(cudaMalloc((void**)&ctx->d_wave_mat, (size_t)grid * 2 * cap * sizeof(uint32_t)));
-        CK(cudaMalloc((void**)&ctx->d_sig_cell, (size_t)grid * scap * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&ctx->d_sig_str, (size_t)grid * scap * sizeof(float)));
-        ctx->grid = grid; ctx->wave_cap = cap; ctx->sig_cap = scap;
+        const size_t warps = (size_t)grid * RR_WARPS;
+        CK(cudaMalloc((void**)&ctx->d_wave_f32, warps * 2 * 6 * cap_w * sizeof(float)));
+        CK(cudaMalloc((void**)&ctx->d_wave_f64, warps * 2 * 2 * cap_w * sizeof(double)));
+        CK(cudaMalloc((void**)&ctx->d_wave_mat, warps * 2 * cap_w * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&ctx->d_sig_cell, warps * scap_w * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&ctx->d_sig_str, warps * scap_w * sizeof(float)));
+        ctx->grid = grid; ctx->wave_cap = cap_w; ctx->sig_cap = scap_w;
     }
     return RR_OK;
 }
@@ -500,7 +500,7 @@ static void fill_params(rr_ctx* ctx, RRFrameParams& P)
     P.multipath_threshold = c.multipath_threshold;
     P.noise_seed = ctx->noise_seed;
     P.wave_f32 = ctx->d_wave_f32; P.wave_f64 = ctx->d_wave_f64; P.wave_mat = ctx->d_wave_mat;
-    P.sig_cell = ctx->d_sig_cell; P.sig_strength = ctx->d_sig_str; P.wave_cap = ctx->wave_cap; P.sig_cap = ctx->sig_cap;
+    P.sig_cell = ctx->d_sig_cell; P.sig_strength = ctx->d_sig_str; P.wave_cap_w = ctx->wave_cap; P.sig_cap_w = ctx->sig_cap;
     P.work_counter = ctx->d_work; P.counters = ctx->d_counters; P.error_flags = ctx->d_errflags;
 }
 
@@ -527,7 +527,7 @@ static int collect(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
     s.kernel_ms = kernel_ms; s.bvh_build_ms = ctx->bvh_build_ms; s.overflow = flags[0];
     if (stats) *stats = s;
     if (flags[1]) return fail(ctx, RR_ERR_OUT_OF_RANGE, "a hit face carries an object id >= n_objects");
-    if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave/signal list overflow (cap %u waves per azimuth); raise rr_set_max_waves_per_azimuth", ctx->wave_cap);
+    if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave/signal list overflow (cap %u waves per warp = %u per azimuth); raise rr_set_max_waves_per_azimuth", ctx->wave_cap, ctx->wave_cap * RR_WARPS);
     return RR_OK;
 }
 
@@ -615,36 +615,49 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
     if (!Tsm) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_debug_trace: NULL pose");
     if ((rc = ensure_scratch(ctx))) return rc;
     const uint32_t Pn = std::max<uint32_t>(1, ctx->model.n_reflections);
-    const uint32_t ccap = ctx->wave_cap * Pn, scap = ctx->sig_cap;
+    const uint32_t ccap = ctx->wave_cap * Pn, scap = ctx->sig_cap;          /* per warp */
     const int C = ctx->cfg.n_cells;
+    const size_t n_cnt = (size_t)RR_N_ANGLES * RR_MAX_PASSES * RR_WARPS * 2;
     rr_cast_record* d_casts = nullptr; rr_signal_record* d_sigs = nullptr; uint32_t* d_cnt = nullptr; float* d_cols = nullptr;
     rr_pose* d_pose = nullptr; uint8_t* d_img = nullptr;
     auto cleanup = [&]() { cudaFree(d_casts); cudaFree(d_sigs); cudaFree(d_cnt); cudaFree(d_cols); cudaFree(d_pose); cudaFree(d_img); };
 #define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
-    CKD(cudaMalloc((void**)&d_casts, (size_t)RR_N_ANGLES * ccap * sizeof(rr_cast_record)));
-    CKD(cudaMalloc((void**)&d_sigs, (size_t)RR_N_ANGLES * scap * sizeof(rr_signal_record)));
-    CKD(cudaMalloc((void**)&d_cnt, (size_t)RR_N_ANGLES * 2 * sizeof(uint32_t)));
+    CKD(cudaMalloc((void**)&d_casts, (size_t)RR_N_ANGLES * RR_WARPS * ccap * sizeof(rr_cast_record)));
+    CKD(cudaMalloc((void**)&d_sigs, (size_t)RR_N_ANGLES * RR_WARPS * scap * sizeof(rr_signal_record)));
+    CKD(cudaMalloc((void**)&d_cnt, n_cnt * sizeof(uint32_t)));
     CKD(cudaMalloc((void**)&d_cols, (size_t)RR_N_ANGLES * C * sizeof(float)));
     CKD(cudaMalloc((void**)&d_pose, sizeof(rr_pose)));
     CKD(cudaMalloc((void**)&d_img, (size_t)C * RR_N_ANGLES));
-    CKD(cudaMemset(d_cnt, 0, (size_t)RR_N_ANGLES * 2 * sizeof(uint32_t)));
+    CKD(cudaMemset(d_cnt, 0, n_cnt * sizeof(uint32_t)));
     CKD(cudaMemcpy(d_pose, Tsm, sizeof(rr_pose), cudaMemcpyHostToDevice));
     RRFrameParams P;
     fill_params(ctx, P);
     P.poses = d_pose; P.n_poses = 1; P.pose_per_azimuth = 0; P.az_begin = 0; P.az_count = RR_N_ANGLES;
     P.frame_id0 = frame_id0; P.out = d_img; P.column_major = 0;
     P.dbg_casts = d_casts; P.dbg_signals = d_sigs; P.dbg_counts = d_cnt; P.dbg_columns = d_cols;
-    P.dbg_cast_cap = ccap; P.dbg_sig_cap = scap;
+    P.dbg_cast_cap_w = ccap; P.dbg_sig_cap_w = scap;
     if ((rc = enqueue(ctx, P, ctx->stream, 1, 1))) { cleanup(); return rc; }
     CKD(cudaStreamSynchronize(ctx->stream));
-    std::vector<uint32_t> cnt(RR_N_ANGLES * 2);
-    CKD(cudaMemcpy(cnt.data(), d_cnt, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    /* re-assemble the reference's list order: for azimuth, for pass, for warp: that warp's (pass) segment */
+    std::vector<uint32_t> cnt(n_cnt);
+    std::vector<rr_cast_record> hc((size_t)RR_N_ANGLES * RR_WARPS * ccap);
+    std::vector<rr_signal_record> hs((size_t)RR_N_ANGLES * RR_WARPS * scap);
+    CKD(cudaMemcpy(cnt.data(), d_cnt, n_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(hc.data(), d_casts, hc.size() * sizeof(rr_cast_record), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(hs.data(), d_sigs, hs.size() * sizeof(rr_signal_record), cudaMemcpyDeviceToHost));
     size_t nc = 0, ns = 0;
     for (int a = 0; a < RR_N_ANGLES; a++) {
-        const size_t c = std::min<size_t>(cnt[2 * a], ccap), s = std::min<size_t>(cnt[2 * a + 1], scap);
-        if (casts && nc + c <= cast_capacity) CKD(cudaMemcpy(casts + nc, d_casts + (size_t)a * ccap, c * sizeof(rr_cast_record), cudaMemcpyDeviceToHost));
-        if (signals && ns + s <= signal_capacity) CKD(cudaMemcpy(signals + ns, d_sigs + (size_t)a * scap, s * sizeof(rr_signal_record), cudaMemcpyDeviceToHost));
-        nc += c; ns += s;
+        uint32_t coff[RR_WARPS] = {0}, soff[RR_WARPS] = {0};
+        for (uint32_t p = 0; p < ctx->model.n_reflections; p++) {
+            for (int w = 0; w < RR_WARPS; w++) {
+                const uint32_t* c2 = &cnt[(((size_t)a * RR_MAX_PASSES + p) * RR_WARPS + w) * 2];
+                for (uint32_t k = 0; k < c2[0]; k++, nc++)
+                    if (casts && nc < cast_capacity && coff[w] + k < ccap) casts[nc] = hc[((size_t)a * RR_WARPS + w) * ccap + coff[w] + k];
+                for (uint32_t k = 0; k < c2[1]; k++, ns++)
+                    if (signals && ns < signal_capacity && soff[w] + k < scap) signals[ns] = hs[((size_t)a * RR_WARPS + w) * scap + soff[w] + k];
+                coff[w] += c2[0]; soff[w] += c2[1];
+            }
+        }
     }
     if (n_casts) *n_casts = nc;
     if (n_signals) *n_signals = ns;

@@ -130,21 +130,26 @@ void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& bn, cons
     out.root_ref = 0;
     if (bn.empty()) {                       /* empty mesh: one node with two empty children */
         RRNode nd; memset(&nd, 0, sizeof(nd));
-        for (int c = 0; c < 2; c++) for (int a = 0; a < 3; a++) { nd.q[6 * c + a] = 65535; nd.q[6 * c + 3 + a] = 0; }
+        for (int k = 0; k < 6; k++) nd.w[k] = 65535u;                /* lo = 65535, hi = 0: empty */
         nd.c0 = nd.c1 = RR_REF_EMPTY;
         out.nodes.push_back(nd);
         for (int a = 0; a < 3; a++) { out.grid_origin[a] = 0.f; out.grid_scale[a] = 1.f; }
         return;
     }
-    /* grid over the padded scene box */
+    /* grid over the padded scene box. pad covers (a) Moeller-Trumbore accepting points a hair outside a triangle and
+     * (b) the rounding of the ray-space plane distances, ~2^-23 * |origin - ray origin| (see rr_internal.h) */
     float pad[3];
+    float ext_max = 0.f;
+    for (int a = 0; a < 3; a++) ext_max = std::max(ext_max, bn[0].hi[a] - bn[0].lo[a]);
     for (int a = 0; a < 3; a++) {
         const float lo = bn[0].lo[a], hi = bn[0].hi[a];
-        pad[a] = 1e-5f * std::max(1.0f, std::max(std::fabs(lo), std::fabs(hi)));
-        out.grid_origin[a] = lo - 2.f * pad[a];
-        out.grid_scale[a] = ((hi - lo) + 4.f * pad[a]) / 65535.0f;
+        pad[a] = std::max(1e-5f * std::max(1.0f, std::max(std::fabs(lo), std::fabs(hi))), ext_max * 0x1p-20f);
+        /* 4 cells of head-room on both sides for the +-1 cell widening below */
+        const float span = (hi - lo) + 4.f * pad[a];
+        out.grid_scale[a] = span / 65527.0f;
+        out.grid_origin[a] = (lo - 2.f * pad[a]) - 4.f * out.grid_scale[a];
     }
-    auto quant = [&](const RRBuildNode& b, uint16_t* q) {
+    auto quant = [&](const RRBuildNode& b, uint32_t* w) {
         for (int a = 0; a < 3; a++) {
             const float o = out.grid_origin[a], s = out.grid_scale[a];
             const float lo = b.lo[a] - pad[a], hi = b.hi[a] + pad[a];
@@ -152,7 +157,8 @@ void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& bn, cons
             ql = std::min(std::max(ql, 0), 65535); qh = std::min(std::max(qh, 0), 65535);
             while (ql > 0 && fmaf((float)ql, s, o) > lo) ql--;          /* conservative under the decode expression */
             while (qh < 65535 && fmaf((float)qh, s, o) < hi) qh++;
-            q[a] = (uint16_t)ql; q[3 + a] = (uint16_t)qh;
+            ql = std::max(ql - 1, 0); qh = std::min(qh + 1, 65535);     /* one cell per side: ray-space rounding */
+            w[a] = (uint32_t)ql | ((uint32_t)qh << 16);
         }
     };
     auto leaf_ref = [&](const RRBuildNode& b) -> uint32_t {
@@ -160,8 +166,8 @@ void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& bn, cons
     };
     if (bn[0].left < 0) {                   /* single-leaf mesh */
         RRNode nd; memset(&nd, 0, sizeof(nd));
-        quant(bn[0], &nd.q[0]);
-        for (int a = 0; a < 3; a++) { nd.q[6 + a] = 65535; nd.q[9 + a] = 0; }
+        quant(bn[0], &nd.w[0]);
+        for (int k = 3; k < 6; k++) nd.w[k] = 65535u;
         nd.c0 = leaf_ref(bn[0]); nd.c1 = RR_REF_EMPTY;
         out.nodes.push_back(nd);
         return;
@@ -182,8 +188,8 @@ void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& bn, cons
         RRNode nd; memset(&nd, 0, sizeof(nd));
         const RRBuildNode& L = bn[bn[i].left];
         const RRBuildNode& R = bn[bn[i].right];
-        quant(L, &nd.q[0]);
-        quant(R, &nd.q[6]);
+        quant(L, &nd.w[0]);
+        quant(R, &nd.w[3]);
         nd.c0 = (L.left >= 0) ? (uint32_t)packed_idx[bn[i].left] : leaf_ref(L);
         nd.c1 = (R.left >= 0) ? (uint32_t)packed_idx[bn[i].right] : leaf_ref(R);
         out.nodes[packed_idx[i]] = nd;

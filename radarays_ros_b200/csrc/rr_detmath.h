@@ -91,29 +91,25 @@ RR_HD double rr_rem_pio2(double x, int* quadrant)
     return r;
 }
 
-RR_HD double rr_sin(double x)
+/* shared front end of sin/cos/tan: kernel values on the reduced argument + quadrant. rr_sin / rr_cos / rr_tan are
+ * pure selections/quotients of (s, c), so evaluating the pair once and deriving several functions from it gives
+ * exactly the bits of the separate calls (the frame kernel does that for sin and tan of the same angle). */
+typedef struct { double s, c; int q; } rr_sincos_t;
+RR_HD rr_sincos_t rr_sincos_parts(double x)
 {
-    if (!(fabs(x) < 1.0e5)) return x - x; /* NaN for inf/NaN/out-of-domain */
-    int q; const double r = rr_rem_pio2(x, &q);
-    const double s = rr_ksin(r), c = rr_kcos(r);
-    return (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+    rr_sincos_t r;
+    if (!(fabs(x) < 1.0e5)) { r.s = x - x; r.c = x - x; r.q = 0; return r; }   /* NaN for inf/NaN/out-of-domain */
+    const double red = rr_rem_pio2(x, &r.q);
+    r.s = rr_ksin(red); r.c = rr_kcos(red);
+    return r;
 }
+RR_HD double rr_sin_of(rr_sincos_t p) { return (p.q == 0) ? p.s : (p.q == 1) ? p.c : (p.q == 2) ? -p.s : -p.c; }
+RR_HD double rr_cos_of(rr_sincos_t p) { return (p.q == 0) ? p.c : (p.q == 1) ? -p.s : (p.q == 2) ? -p.c : p.s; }
+RR_HD double rr_tan_of(rr_sincos_t p) { return (p.q & 1) ? (-p.c / p.s) : (p.s / p.c); }
 
-RR_HD double rr_cos(double x)
-{
-    if (!(fabs(x) < 1.0e5)) return x - x;
-    int q; const double r = rr_rem_pio2(x, &q);
-    const double s = rr_ksin(r), c = rr_kcos(r);
-    return (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
-}
-
-RR_HD double rr_tan(double x)
-{
-    if (!(fabs(x) < 1.0e5)) return x - x;
-    int q; const double r = rr_rem_pio2(x, &q);
-    const double s = rr_ksin(r), c = rr_kcos(r);
-    return (q & 1) ? (-c / s) : (s / c);
-}
+RR_HD double rr_sin(double x) { return rr_sin_of(rr_sincos_parts(x)); }
+RR_HD double rr_cos(double x) { return rr_cos_of(rr_sincos_parts(x)); }
+RR_HD double rr_tan(double x) { return rr_tan_of(rr_sincos_parts(x)); }
 
 /* ------------------------------------------------------------------------------------------------
  * asin / acos (double).  asin(x) = x + x*z*P(z), z = x^2 <= 1/4, exact Maclaurin coefficients.

@@ -8,16 +8,22 @@
 #include "rr_detmath.h"
 
 /* ---- compact BVH --------------------------------------------------------------------------------
- * 32-byte binary node: both child boxes quantised to 16 bit on one global grid
- *     x = fmaf((float)q, grid_scale, grid_origin)      (conservative: lo rounded down, hi rounded up,
- *                                                        verified with this exact expression at build time)
- * so a node is ONE 32-byte sector (two LDG.128), and the traversal stack holds bare 4-byte refs.
+ * 32-byte binary node = ONE 32-byte sector (two LDG.128). Both child boxes are quantised to 16 bit on one
+ * global grid, x(q) = grid_origin + q * grid_scale, and stored per axis as (lo | hi << 16) so that a
+ * per-ray byte-permute selector picks the NEAR or FAR plane of an axis in one PRMT:
+ *     w[0..2] = child0 x,y,z   w[3..5] = child1 x,y,z   c0, c1 = child refs
+ * Traversal evaluates plane distances in ray space with one FFMA per plane,
+ *     t = f * A + B',  f = float(2^23 + q) (bit pattern 0x4B000000 | q),  A = scale/d,  B' = (origin - o)/d - 2^23 * A,
+ * whose rounding amounts to moving the ray origin by < 1 grid cell per axis; the packer therefore widens every
+ * quantised box by one cell per side (on top of conservative rounding + padding), which keeps the walk
+ * conservative. The boxes only steer the walk; hits are decided by rr_ray_triangle on the exact ray.
+ * The traversal stack holds bare 4-byte refs.
  * Child ref: bit31 = leaf. leaf: bits[30:28] = count-1 (1..8 triangles), bits[27:0] = first triangle.
  *            inner: node index. RR_REF_EMPTY = child absent (only for meshes with < 2 leaves).
  * Triangles are stored in leaf order as 3 x float4 (48 B): (v0.xyz, face_id) (e1.xyz, object_id) (e2.xyz, 0).
  */
 struct __attribute__((aligned(32))) RRNode {
-    uint16_t q[12];      /* child0: lo.xyz hi.xyz, child1: lo.xyz hi.xyz */
+    uint32_t w[6];       /* (lo | hi << 16) for child0 x,y,z then child1 x,y,z */
     uint32_t c0, c1;
 };
 #define RR_REF_LEAF   0x80000000u
@@ -35,6 +41,8 @@ struct RRBuildNode {
 /* ---- kernel parameter block ---------------------------------------------------------------------*/
 #define RR_MAX_DENOISE 256
 #define RR_BLOCK 256
+#define RR_WARPS (RR_BLOCK / 32)
+#define RR_MAX_PASSES 20         /* cfg/RadarModel.cfg:27 n_reflections <= 20 */
 
 struct RRFrameParams {
     /* scene */
@@ -66,23 +74,23 @@ struct RRFrameParams {
     /* output */
     uint8_t* out;                  /* row-major [pose][cell][400] or column-major [pose][az-az_begin][cell] */
     int32_t column_major;
-    /* per-CTA scratch */
-    float* wave_f32;               /* [cta][2 lists][6 comps][cap] */
-    double* wave_f64;              /* [cta][2 lists][2 comps][cap] energy,time */
-    uint32_t* wave_mat;            /* [cta][2 lists][cap] */
-    int32_t* sig_cell;             /* [cta][sig_cap] */
-    float* sig_strength;           /* [cta][sig_cap] */
-    uint32_t wave_cap, sig_cap;
+    /* per-warp scratch (8 warps per CTA; SoA so that lanes access consecutive words) */
+    float* wave_f32;               /* [cta][warp][2 lists][6 comps][wave_cap_w] orig.xyz dir.xyz */
+    double* wave_f64;              /* [cta][warp][2 lists][2 comps][wave_cap_w] energy, time */
+    uint32_t* wave_mat;            /* [cta][warp][2 lists][wave_cap_w] material id */
+    int32_t* sig_cell;             /* [cta][warp][sig_cap_w] returns in generation order */
+    float* sig_strength;           /* [cta][warp][sig_cap_w] */
+    uint32_t wave_cap_w, sig_cap_w;
     /* control + counters */
     uint32_t* work_counter;
     unsigned long long* counters;  /* [0] casts [1] hits [2] signals [3] nodes [4] tris [5] max_waves */
     int32_t* error_flags;          /* [0] wave overflow [1] object/material id out of range */
     /* debug (rr_debug_trace) */
-    rr_cast_record* dbg_casts;     /* [az][dbg_cast_cap] */
-    rr_signal_record* dbg_signals; /* [az][dbg_sig_cap] */
-    uint32_t* dbg_counts;          /* [az][2] */
+    rr_cast_record* dbg_casts;     /* [az][warp][dbg_cast_cap_w], per warp in (pass, list) order */
+    rr_signal_record* dbg_signals; /* [az][warp][dbg_sig_cap_w] */
+    uint32_t* dbg_counts;          /* [az][RR_MAX_PASSES][warp][2] = (casts, signals) of that (pass, warp) segment */
     float* dbg_columns;            /* [az][cell] */
-    uint32_t dbg_cast_cap, dbg_sig_cap;
+    uint32_t dbg_cast_cap_w, dbg_sig_cap_w;
 };
 
 #endif

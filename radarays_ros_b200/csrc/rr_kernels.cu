@@ -12,8 +12,10 @@
  */
 #include "rr_internal.h"
 
-#define RR_WARPS (RR_BLOCK / 32)
 #define RR_FULL 0xffffffffu
+#ifndef RR_MIN_BLOCKS
+#define RR_MIN_BLOCKS 4            /* resident CTAs per SM the register allocation is tuned for */
+#endif
 
 /* Wave state. Quirk kept on purpose: the reference never updates DirectedWave::velocity on the waves it pushes
  * (RadarCPU.cpp:285-286,364-365 copy only dir and energy out of fresnel()'s result), so every wave travels with
@@ -29,7 +31,18 @@ struct RRWave {
 /* ------------------------------------------------------------------------------------------------
  * closest hit: smallest t, ties -> lowest face id (rr_detmath.h). Returns triangle SLOT or -1.
  * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ float rr_q16(uint32_t w, int hi) { return (float)(hi ? (w >> 16) : (w & 0xffffu)); }
+/* reciprocal that stays finite for zero components: the slab planes then sit at -/+ 1e30-ish, on the same side when
+ * the origin is outside the slab (reject), on opposite sides when inside (accept) — conservative, and no 0*inf NaNs */
+__device__ __forceinline__ float rr_safe_rcp(float d) { return 1.0f / ((fabsf(d) > 1e-30f) ? d : copysignf(1e-30f, d)); }
+
+/* one PRMT: picks the low or high u16 of `w` (selector 0x7610 / 0x7632) under the exponent bytes of 2^23,
+ * i.e. returns the float 8388608 + q without any int->float conversion */
+__device__ __forceinline__ float rr_plane(uint32_t w, uint32_t sel, uint32_t magic)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "r"(sel));
+    return __uint_as_float(r);
+}
 
 template <bool STATS>
 __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const float4* __restrict__ tris,
@@ -37,9 +50,18 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
                                         rr_vec3 o, rr_vec3 d, float tmax, float& t_hit, int& face_hit,
                                         unsigned& n_nodes, unsigned& n_tris)
 {
-    const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
-    const float gox = go[0], goy = go[1], goz = go[2];
-    const float gsx = gs[0], gsy = gs[1], gsz = gs[2];
+    /* plane distance in ray space (rr_internal.h): t = f*A + B', f = 2^23 + q. One PRMT + one FFMA per plane; the
+     * near/far plane of each axis is chosen by the per-ray selectors, so no per-axis min/max is needed. */
+    const float ix = rr_safe_rcp(d.x), iy = rr_safe_rcp(d.y), iz = rr_safe_rcp(d.z);
+    const float sax = gs[0] * ix, say = gs[1] * iy, saz = gs[2] * iz;
+    const float sbx = fmaf(-8388608.0f, sax, (go[0] - o.x) * ix);
+    const float sby = fmaf(-8388608.0f, say, (go[1] - o.y) * iy);
+    const float sbz = fmaf(-8388608.0f, saz, (go[2] - o.z) * iz);
+    const uint32_t nx = (ix >= 0.f) ? 0x7610u : 0x7632u, fx = nx ^ 0x0022u;
+    const uint32_t ny = (iy >= 0.f) ? 0x7610u : 0x7632u, fy = ny ^ 0x0022u;
+    const uint32_t nz = (iz >= 0.f) ? 0x7610u : 0x7632u, fz = nz ^ 0x0022u;
+    uint32_t magic;
+    asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));   /* kept in a register: PRMT's third operand */
     uint32_t stack[RR_STACK_SIZE];
     int sp = 0;
     uint32_t cur = root_ref;
@@ -50,31 +72,19 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
     while (true) {
         if (!(cur & RR_REF_LEAF)) {
             const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
-            const uint4 a = __ldg(np);
-            const uint4 b = __ldg(np + 1);
+            const uint4 a = __ldg(np);           /* c0.x c0.y c0.z c1.x */
+            const uint4 b = __ldg(np + 1);       /* c1.y c1.z ref0 ref1 */
             if (STATS) n_nodes++;
-            /* child 0: lo = (a.x.lo, a.x.hi, a.y.lo) hi = (a.y.hi, a.z.lo, a.z.hi) */
-            float t0n, t0f, t1n, t1f;
-            {
-                const float lx = fmaf(rr_q16(a.x, 0), gsx, gox), ly = fmaf(rr_q16(a.x, 1), gsy, goy), lz = fmaf(rr_q16(a.y, 0), gsz, goz);
-                const float hx = fmaf(rr_q16(a.y, 1), gsx, gox), hy = fmaf(rr_q16(a.z, 0), gsy, goy), hz = fmaf(rr_q16(a.z, 1), gsz, goz);
-                const float ax = (lx - o.x) * ix, bx = (hx - o.x) * ix;
-                const float ay = (ly - o.y) * iy, by = (hy - o.y) * iy;
-                const float az = (lz - o.z) * iz, bz = (hz - o.z) * iz;
-                t0n = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-                t0f = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), limit));
-            }
-            {
-                const float lx = fmaf(rr_q16(a.w, 0), gsx, gox), ly = fmaf(rr_q16(a.w, 1), gsy, goy), lz = fmaf(rr_q16(b.x, 0), gsz, goz);
-                const float hx = fmaf(rr_q16(b.x, 1), gsx, gox), hy = fmaf(rr_q16(b.y, 0), gsy, goy), hz = fmaf(rr_q16(b.y, 1), gsz, goz);
-                const float ax = (lx - o.x) * ix, bx = (hx - o.x) * ix;
-                const float ay = (ly - o.y) * iy, by = (hy - o.y) * iy;
-                const float az = (lz - o.z) * iz, bz = (hz - o.z) * iz;
-                t1n = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-                t1f = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), limit));
-            }
-            const bool h0 = (t0n <= t0f * 1.0000005f) && (b.z != RR_REF_EMPTY);
-            const bool h1 = (t1n <= t1f * 1.0000005f) && (b.w != RR_REF_EMPTY);
+            const float t0n = fmaxf(fmaxf(fmaf(rr_plane(a.x, nx, magic), sax, sbx), fmaf(rr_plane(a.y, ny, magic), say, sby)),
+                                    fmaxf(fmaf(rr_plane(a.z, nz, magic), saz, sbz), 0.0f));
+            const float t0f = fminf(fminf(fmaf(rr_plane(a.x, fx, magic), sax, sbx), fmaf(rr_plane(a.y, fy, magic), say, sby)),
+                                    fminf(fmaf(rr_plane(a.z, fz, magic), saz, sbz), limit));
+            const float t1n = fmaxf(fmaxf(fmaf(rr_plane(a.w, nx, magic), sax, sbx), fmaf(rr_plane(b.x, ny, magic), say, sby)),
+                                    fmaxf(fmaf(rr_plane(b.y, nz, magic), saz, sbz), 0.0f));
+            const float t1f = fminf(fminf(fmaf(rr_plane(a.w, fx, magic), sax, sbx), fmaf(rr_plane(b.x, fy, magic), say, sby)),
+                                    fminf(fmaf(rr_plane(b.y, fz, magic), saz, sbz), limit));
+            const bool h0 = (t0n <= t0f) && (b.z != RR_REF_EMPTY);
+            const bool h1 = (t1n <= t1f) && (b.w != RR_REF_EMPTY);
             if (h0 && h1) {
                 const bool first0 = t0n <= t1n;
                 cur = first0 ? b.z : b.w;
@@ -111,36 +121,6 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
     t_hit = best_t;
     face_hit = best_face;
     return best_slot;
-}
-
-/* ------------------------------------------------------------------------------------------------
- * block-wide exclusive scan of one 32-bit value per thread (two 16-bit fields are scanned at once)
- * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ uint32_t rr_block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t nb = __shfl_up_sync(RR_FULL, incl, off);
-        if (lane >= off) incl += nb;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t x = (lane < RR_WARPS) ? s_warp[lane] : 0u;
-#pragma unroll
-        for (int off = 1; off < RR_WARPS; off <<= 1) {
-            const uint32_t nb = __shfl_up_sync(RR_FULL, x, off);
-            if (lane >= off) x += nb;
-        }
-        if (lane < RR_WARPS) s_warp[lane] = x;
-    }
-    __syncthreads();
-    const uint32_t prefix = (wid > 0) ? s_warp[wid - 1] : 0u;
-    total = s_warp[RR_WARPS - 1];
-    __syncthreads();
-    return prefix + incl - v;
 }
 
 /* Ken Perlin's reference permutation (image_algorithms.h:14-50 holds it twice back to back) */
@@ -199,35 +179,51 @@ __device__ __forceinline__ uint8_t rr_to_u8(float v)
 
 /* ------------------------------------------------------------------------------------------------
  * the fused frame kernel
+ *
+ * One persistent CTA owns one (pose, azimuth) work item at a time. Inside it the 8 warps are DECOUPLED while
+ * tracing: warp w owns the contiguous sample chunk [w*spw, (w+1)*spw) and walks its wave tree through all passes
+ * on its own (ballot/popc compaction into per-warp ping-pong lists, no block barrier). The reference's list order
+ * (RadarCPU.cpp:243,290,322,369: pass-major, parents in order, reflection before refraction) is kept because by
+ * induction every warp's waves form one contiguous run of each pass's list: the canonical order is
+ * "for pass: for warp: that warp's (pass) segment", which the draw phase replays from a segment table.
  * ---------------------------------------------------------------------------------------------- */
 template <bool STATS, bool DEBUG>
-__global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams P)
+__global__ void __launch_bounds__(RR_BLOCK, RR_MIN_BLOCKS) rr_frame_kernel(const RRFrameParams P)
 {
     extern __shared__ float s_col[];                     /* n_cells floats: this azimuth's range column */
     __shared__ float s_weights[RR_MAX_DENOISE];
     __shared__ unsigned char s_perm[256];
-    __shared__ uint32_t s_scan[RR_WARPS];
+    __shared__ uint32_t s_seg_start[RR_MAX_PASSES][RR_WARPS];   /* per-(pass, warp) run inside the warp's signal buffer */
+    __shared__ uint32_t s_seg_count[RR_MAX_PASSES][RR_WARPS];
+    __shared__ uint32_t s_pass_waves[RR_MAX_PASSES];
     __shared__ float s_red[RR_WARPS];
-    __shared__ uint32_t s_item, s_next_base, s_sig_base;
+    __shared__ uint32_t s_item, s_hits;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? P.denoise_weights[i] : 0.f;
     for (int i = tid; i < 256; i += RR_BLOCK) s_perm[i] = c_perlin_perm[i];
 
-    const uint32_t cap = P.wave_cap, scap = P.sig_cap;
-    float* wf = P.wave_f32 + (size_t)blockIdx.x * 2 * 6 * cap;
-    double* wd = P.wave_f64 + (size_t)blockIdx.x * 2 * 2 * cap;
-    uint32_t* wm = P.wave_mat + (size_t)blockIdx.x * 2 * cap;
-    int32_t* sg_cell = P.sig_cell + (size_t)blockIdx.x * scap;
-    float* sg_str = P.sig_strength + (size_t)blockIdx.x * scap;
+    const uint32_t cap = P.wave_cap_w, scap = P.sig_cap_w;
+    const size_t wslot = (size_t)blockIdx.x * RR_WARPS + wid;
+    float* wf = P.wave_f32 + wslot * 2 * 6 * cap;
+    double* wd = P.wave_f64 + wslot * 2 * 2 * cap;
+    uint32_t* wm = P.wave_mat + wslot * 2 * cap;
+    int32_t* sg_cell = P.sig_cell + wslot * scap;
+    float* sg_str = P.sig_strength + wslot * scap;
     const int C = P.n_cells;
+    const int n_passes = P.n_passes;
     const uint32_t total_items = (uint32_t)P.n_poses * (uint32_t)P.az_count;
     const float go[3] = {P.grid_origin[0], P.grid_origin[1], P.grid_origin[2]};
     const float gs[3] = {P.grid_scale[0], P.grid_scale[1], P.grid_scale[2]};
+    const uint32_t spw = ((uint32_t)P.n_samples + RR_WARPS - 1) / RR_WARPS;      /* samples per warp */
+    const uint32_t s_begin = min((uint32_t)P.n_samples, (uint32_t)wid * spw);
+    const uint32_t s_count = min((uint32_t)P.n_samples, s_begin + spw) - s_begin;
 
     while (true) {
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(P.work_counter, 1u);
+        if (tid == 0) { s_item = atomicAdd(P.work_counter, 1u); s_hits = 0; }
+        if (tid < RR_MAX_PASSES) s_pass_waves[tid] = 0;
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= total_items) break;
@@ -244,32 +240,28 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
         const rr_vec3 T = rr_add(rr_qrot(Rsm, rr_v3(0.f, 0.f, 0.f)), rr_v3(ps.tx, ps.ty, ps.tz));
 
         for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
-        if (tid == 0) s_sig_base = 0;
 
-        uint32_t n_cur = (uint32_t)P.n_samples;
+        /* ================= trace: this warp's samples through all passes, no block barrier ================= */
+        uint32_t n_cur = s_count;
         int cur = 0;
-        uint32_t cast_base = 0;
-        unsigned long long item_hits = 0;
+        uint32_t sig_off = 0, warp_hits = 0, warp_casts = 0;
         unsigned stat_nodes = 0, stat_tris = 0;
-        uint32_t max_waves = n_cur;
 
-        for (int pass = 0; pass < P.n_passes; pass++) {
-            __syncthreads();
-            if (tid == 0) s_next_base = 0;
-            __syncthreads();
+        for (int pass = 0; pass < n_passes; pass++) {
+            const bool last_pass = (pass == n_passes - 1);
             const float* cf = wf + (size_t)cur * 6 * cap;
             const double* cd = wd + (size_t)cur * 2 * cap;
             const uint32_t* cm = wm + (size_t)cur * cap;
             float* nf = wf + (size_t)(cur ^ 1) * 6 * cap;
             double* ndp = wd + (size_t)(cur ^ 1) * 2 * cap;
             uint32_t* nm = wm + (size_t)(cur ^ 1) * cap;
+            const uint32_t seg_start = sig_off;
+            uint32_t next_n = 0;
 
-            const bool last_pass = (pass == P.n_passes - 1);
-            for (uint32_t base = 0; base < n_cur; base += RR_BLOCK) {
-                const uint32_t i = base + tid;
+            for (uint32_t base = 0; base < n_cur; base += 32) {
+                const uint32_t i = base + lane;
                 const bool active = i < n_cur;
                 uint32_t n_child = 0, n_sig = 0;
-                /* results to be appended in order */
                 rr_vec3 c_o = rr_v3(0, 0, 0), c_d0 = c_o, c_d1 = c_o;
                 double c_time = 0, c_e0 = 0, c_e1 = 0;
                 uint32_t c_m0 = 0, c_m1 = 0;
@@ -282,8 +274,9 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
                 if (active) {
                     RRWave w;
                     if (pass == 0) {                      /* RadarCPU.cpp:106-114,184 */
+                        const uint32_t smp = s_begin + i;
                         w.o = rr_v3(0.f, 0.f, 0.f);
-                        w.d = rr_v3(P.beam_dirs[3 * i], P.beam_dirs[3 * i + 1], P.beam_dirs[3 * i + 2]);
+                        w.d = rr_v3(P.beam_dirs[3 * smp], P.beam_dirs[3 * smp + 1], P.beam_dirs[3 * smp + 2]);
                         w.energy = 1.0; w.time = 0.0; w.mat = 0u;
                     } else {
                         w.o = rr_v3(cf[0 * cap + i], cf[1 * cap + i], cf[2 * cap + i]);
@@ -325,7 +318,8 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
                             /* Snell/Fresnel (radar_algorithms.h:55-139): n1 := v2, n2 := v1 */
                             const double n1 = (double)v_t, n2 = wave_v;
                             const float cos_i = rr_dot(rr_neg(w.d), n);
-                            const double th_i = (double)rr_acosf(cos_i);
+                            const float th_if = rr_acosf(cos_i);
+                            const double th_i = (double)th_if;
                             const rr_vec3 d_refl = rr_add(w.d, rr_muls(rr_muls(n, 2.0f), rr_dot(rr_neg(n), w.d)));
                             rr_vec3 d_refr = rr_v3(0.f, 0.f, 0.f);
                             rr_vec3 nn = n;
@@ -351,9 +345,9 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
                             } else if (th_sum > M_PI - 0.0001) {
                                 rs = 1.0; rp = 1.0;
                             } else {
-                                const double th_dif = th_i - th_t;
-                                rs = -rr_sin(th_dif) / rr_sin(th_sum);
-                                rp = rr_tan(th_dif) / rr_tan(th_sum);
+                                const rr_sincos_t pd = rr_sincos_parts(th_i - th_t), psum = rr_sincos_parts(th_sum);
+                                rs = -rr_sin_of(pd) / rr_sin_of(psum);
+                                rp = rr_tan_of(pd) / rr_tan_of(psum);
                             }
                             const double Reff = 0.5 * (rs * rs) + (1.0 - 0.5) * (rp * rp);
                             const double Teff = 1.0 - Reff;
@@ -365,7 +359,6 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
                             if (e_refl > thr) {                                /* RadarCPU.cpp:288 */
                                 keep0 = true; c_d0 = d_refl; c_e0 = e_refl; c_m0 = w.mat;
                                 if (w.mat == air) {                            /* :302 — return to the sensor */
-                                    const float th_if = (float)(double)rr_acosf(rr_dot(rr_neg(w.d), n));
                                     const float e_f = (float)e_refl;
                                     {   /* BRDF, radar_algorithms.h:168-187: (A, B, C) = (ambient, diffuse, specular) */
                                         const float lobe = rr_powf(rr_cosf(th_if), mt.w);
@@ -404,15 +397,15 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
                     }
                 }
 
-                item_hits += (unsigned long long)__syncthreads_count(hit ? 1 : 0);
-                /* the reference also builds waves_new in its last pass and then drops it (RadarCPU.cpp:380-389);
+                /* ordered compaction inside the warp (reflection before refraction, parents in list order).
+                 * The reference also builds waves_new in its last pass and drops it (RadarCPU.cpp:380-389):
                  * nothing traces those waves, so the last pass appends none (n_children is still reported). */
                 if (last_pass) { keep0 = false; keep1 = false; }
-                uint32_t tot;
-                const uint32_t excl = rr_block_excl_scan((last_pass ? 0u : n_child) | (n_sig << 16), s_scan, tot);
-                const uint32_t nb = s_next_base, sb = s_sig_base;
-                uint32_t co = nb + (excl & 0xffffu);
-                const uint32_t so = sb + (excl >> 16);
+                const uint32_t m0 = __ballot_sync(RR_FULL, keep0), m1 = __ballot_sync(RR_FULL, keep1);
+                const uint32_t ms0 = __ballot_sync(RR_FULL, n_sig >= 1), ms1 = __ballot_sync(RR_FULL, n_sig >= 2);
+                warp_hits += __popc(__ballot_sync(RR_FULL, hit));
+                uint32_t co = next_n + __popc(m0 & lt_mask) + __popc(m1 & lt_mask);
+                const uint32_t so = sig_off + __popc(ms0 & lt_mask) + __popc(ms1 & lt_mask);
                 const float skip = 0.001f;                                     /* RadarCPU.cpp:374-378 */
                 if (keep0) {
                     if (co < cap) {
@@ -437,70 +430,89 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
                     if (so < scap) { sg_cell[so] = sig_cell0; sg_str[so] = sig_s0; }
                     if (n_sig > 1 && so + 1 < scap) { sg_cell[so + 1] = sig_cell1; sg_str[so + 1] = sig_s1; }
                     if (DEBUG) {
-                        if (so < P.dbg_sig_cap) {
+                        rr_signal_record* ds = P.dbg_signals + ((size_t)az * RR_WARPS + wid) * P.dbg_sig_cap_w;
+                        if (so < P.dbg_sig_cap_w) {
                             rr_signal_record r; r.azimuth = az; r.cell = sig_cell0; r.strength = sig_s0; r.time = sig_t0;
-                            P.dbg_signals[(size_t)az * P.dbg_sig_cap + so] = r;
+                            ds[so] = r;
                         }
-                        if (n_sig > 1 && so + 1 < P.dbg_sig_cap) {
+                        if (n_sig > 1 && so + 1 < P.dbg_sig_cap_w) {
                             rr_signal_record r; r.azimuth = az; r.cell = sig_cell1; r.strength = sig_s1; r.time = sig_t1;
-                            P.dbg_signals[(size_t)az * P.dbg_sig_cap + so + 1] = r;
+                            ds[so + 1] = r;
                         }
                     }
                 }
-                if (DEBUG && active && cast_base + i < P.dbg_cast_cap) {
+                if (DEBUG && active && warp_casts + i < P.dbg_cast_cap_w) {
                     rr_cast_record r; r.azimuth = az; r.pass = pass; r.face_id = hit ? face : -1;
                     r.range = hit ? range : 0.f; r.energy = dbg_energy; r.n_children = (int)n_child;
-                    P.dbg_casts[(size_t)az * P.dbg_cast_cap + cast_base + i] = r;
+                    P.dbg_casts[((size_t)az * RR_WARPS + wid) * P.dbg_cast_cap_w + warp_casts + i] = r;
                 }
-                __syncthreads();
-                if (tid == 0) { s_next_base = nb + (tot & 0xffffu); s_sig_base = sb + (tot >> 16); }
-                __syncthreads();
+                next_n += __popc(m0) + __popc(m1);
+                sig_off += __popc(ms0) + __popc(ms1);
             }
-            cast_base += n_cur;
-            const uint32_t produced = s_next_base;
-            if (produced > cap && tid == 0) atomicExch(&P.error_flags[0], 1);
-            n_cur = produced < cap ? produced : cap;
-            if (n_cur > max_waves) max_waves = n_cur;
+            if (lane == 0) {
+                s_seg_start[pass][wid] = seg_start;
+                s_seg_count[pass][wid] = min(sig_off, scap) - min(seg_start, scap);
+                atomicAdd(&s_pass_waves[pass], n_cur);
+                if (DEBUG) {
+                    uint32_t* dc = P.dbg_counts + (((size_t)az * RR_MAX_PASSES + pass) * RR_WARPS + wid) * 2;
+                    dc[0] = n_cur; dc[1] = s_seg_count[pass][wid];
+                }
+            }
+            warp_casts += n_cur;
+            if ((next_n > cap || sig_off > scap) && lane == 0) atomicExch(&P.error_flags[0], 1);
+            n_cur = min(next_n, cap);
             cur ^= 1;
+            __syncwarp();                                /* children written by other lanes are read next pass */
         }
+        if (lane == 0) atomicAdd(&s_hits, warp_hits);
         __syncthreads();
-        uint32_t n_sigs = s_sig_base;
-        if (n_sigs > scap) { if (tid == 0) atomicExch(&P.error_flags[0], 1); n_sigs = scap; }
-        if (DEBUG && tid == 0) { P.dbg_counts[2 * az] = cast_base; P.dbg_counts[2 * az + 1] = n_sigs; }
-        __threadfence_block();
 
-        /* ---- signals -> column, RadarCPU.cpp:402-450. Bins are partitioned over the warps; every warp walks
-         * the signal list in the reference's order, so each bin sees its additions in exactly that order. */
+        /* ================= signals -> column (RadarCPU.cpp:402-450), in the reference's order =================
+         * Bins are dealt to the warps in 32-bin granules, round-robin (granule G belongs to warp G % 8, bin g to
+         * lane g % 32), so a bin always has the same owner thread and sees its additions in program order = list
+         * order; a W <= 200 wide splat touches at most one granule per warp. Every warp replays the segment table;
+         * 32 signals are tested at once and only the ones touching this warp's granules are applied. */
         float m = 0.0f;
         {
-            const int chunk = (C + RR_WARPS - 1) / RR_WARPS;
-            const int b0 = wid * chunk, b1 = min(C, b0 + chunk);
-            const int W = P.denoise_width, mode = P.denoise_mode;
-            for (uint32_t s = 0; s < n_sigs; s++) {
-                const int cell = sg_cell[s];
-                if (!(cell < C)) continue;
-                const float str = sg_str[s];
-                if (P.denoise_on) {
-                    if (cell < -RR_MAX_DENOISE) continue;
-                    const int start = cell - mode;
-                    const int lo = max(start, max(b0, 1));                     /* glob_id > 0, :424 */
-                    const int hi = min(start + W, b1);
-                    if (lo >= hi) continue;
-                    for (int g = lo + lane; g < hi; g += 32) {
-                        const float v = (float)((double)s_col[g] + (double)str * (double)s_weights[g - start]);
-                        s_col[g] = v;
-                        if (v > m) m = v;
-                    }
-                    __syncwarp();
-                } else {
-                    if (cell >= b0 && cell < b1 && cell >= 0) {
-                        if (lane == 0) {
-                            const float old = s_col[cell];
-                            const float v = (old < str) ? str : old;           /* std::max(old, strength) */
-                            s_col[cell] = v;
-                            if (v > m) m = v;
+            const int W = P.denoise_on ? P.denoise_width : 1;
+            const int mode = P.denoise_on ? P.denoise_mode : 0;
+            const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
+            for (int pass = 0; pass < n_passes; pass++) {
+                for (int sw = 0; sw < RR_WARPS; sw++) {
+                    const uint32_t cnt = s_seg_count[pass][sw];
+                    if (cnt == 0) continue;
+                    const size_t soff = ((size_t)blockIdx.x * RR_WARPS + sw) * scap + s_seg_start[pass][sw];
+                    const int32_t* pc = P.sig_cell + soff;
+                    const float* pst = P.sig_strength + soff;
+                    for (uint32_t base = 0; base < cnt; base += 32) {
+                        const bool valid = base + lane < cnt;
+                        const int cell = valid ? pc[base + lane] : 0;
+                        const float str = valid ? pst[base + lane] : 0.f;
+                        /* cell < C (:414); very negative cells (time = -inf/NaN) can not reach a bin */
+                        bool rel = valid && (cell < C) && (cell > -RR_MAX_DENOISE - 1);
+                        const int start = cell - mode;
+                        const int gs0 = start >> 5, ge0 = (start + W - 1) >> 5;
+                        rel = rel && (gs0 + ((wid - gs0) & (RR_WARPS - 1)) <= ge0);
+                        uint32_t mask = __ballot_sync(RR_FULL, rel);
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int st = __shfl_sync(RR_FULL, start, j);
+                            const float sv = __shfl_sync(RR_FULL, str, j);
+                            const int g0 = st >> 5;
+                            const int g = ((g0 + ((wid - g0) & (RR_WARPS - 1))) << 5) + lane;
+                            if (g >= max(st, lo_bin) && g < min(st + W, C)) {
+                                float v;
+                                if (P.denoise_on) {
+                                    v = (float)((double)s_col[g] + (double)sv * (double)s_weights[g - st]);
+                                } else {
+                                    const float old = s_col[g];
+                                    v = (old < sv) ? sv : old;                 /* std::max(old, strength), :439 */
+                                }
+                                s_col[g] = v;
+                                if (v > m) m = v;                              /* running max_val, :428-431 */
+                            }
                         }
-                        __syncwarp();
                     }
                 }
             }
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
 #pragma unroll
         for (int k = 0; k < RR_WARPS; k++) if (s_red[k] > max_val) max_val = s_red[k];
 
-        /* ---- energy_max, ambient noise, normalise, mono8 (RadarCPU.cpp:453-542) */
+        /* ================= energy_max, ambient noise, normalise, mono8 (RadarCPU.cpp:453-542) ================= */
         const int col = (P.scroll_image + az) % RR_N_ANGLES;
         const uint64_t frame_id = P.frame_id0 + (uint64_t)pose_i;
         const float signal_amp = max_val - 0.0f;
@@ -555,7 +567,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
             if (P.column_major) out[i] = px; else out[(size_t)i * RR_N_ANGLES] = px;
         }
 
-        /* ---- counters */
+        /* ================= counters ================= */
         if (STATS) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -568,10 +580,16 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_frame_kernel(const RRFrameParams 
             }
         }
         if (tid == 0) {
-            atomicAdd(&P.counters[0], (unsigned long long)cast_base);
-            atomicAdd(&P.counters[1], item_hits);
-            atomicAdd(&P.counters[2], (unsigned long long)n_sigs);
-            atomicMax(&P.counters[5], (unsigned long long)max_waves);
+            unsigned long long casts = 0, sigs = 0, mw = 0;
+            for (int p2 = 0; p2 < n_passes; p2++) {
+                casts += s_pass_waves[p2];
+                if (s_pass_waves[p2] > mw) mw = s_pass_waves[p2];
+                for (int w2 = 0; w2 < RR_WARPS; w2++) sigs += s_seg_count[p2][w2];
+            }
+            atomicAdd(&P.counters[0], casts);
+            atomicAdd(&P.counters[1], (unsigned long long)s_hits);
+            atomicAdd(&P.counters[2], sigs);
+            atomicMax(&P.counters[5], mw);
         }
     }
 }
