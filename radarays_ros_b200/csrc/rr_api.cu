@@ -1,6 +1,7 @@
 /* rr_api.cu — C ABI of libradarays_b200.so (include/radarays_b200.h). Host side only: context, parameter
  * marshalling, BVH build dispatch, launches. No CPU implementation of the hot path lives here: every
  * compute entry point launches rr_kernels.cu and fails loudly without a CUDA device. */
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -154,9 +155,26 @@ rr_quat euler_to_quat(float roll, float pitch, float yaw)     /* rmagine EulerAn
 
 /* sample_cone_local (radar_algorithms.cpp:248-294) with Philox4x32-10 keyed by (seed, sample) in place of
  * std::mt19937(random_device): word0 -> angle, word1 -> radius, word2 -> normal via radar_math.h:47-50. */
+/* 2 x 16 bit Morton code of the beam-local angles, quantised over [-4r, 4r) */
+uint32_t beam_morton_key(float alpha, float beta, float radius)
+{
+    auto q16 = [&](float v) -> uint32_t {
+        float t = floorf((v / (radius * 8.0f) + 0.5f) * 65536.0f);
+        if (!(t >= 0.0f)) t = 0.0f;
+        if (t > 65535.0f) t = 65535.0f;
+        return (uint32_t)t;
+    };
+    auto spread = [](uint32_t x) -> uint32_t {
+        x &= 0xffffu; x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu;
+        x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u; return x;
+    };
+    return spread(q16(alpha)) | (spread(q16(beta)) << 1);
+}
+
 void draw_beam_samples(float width, int n, int dist, float p_in_cone, uint64_t seed, std::vector<float>& out)
 {
     out.resize((size_t)3 * n);
+    std::vector<uint64_t> keys(n);
     const float z = (float)(M_SQRT2 * erfinv_f32(p_in_cone));
     const float radius = (float)(width / 2.0);
     for (int i = 0; i < n; i++) {
@@ -179,7 +197,17 @@ void draw_beam_samples(float width, int n, int dist, float p_in_cone, uint64_t s
         const float alpha = rad * cosf(ang), beta = rad * sinf(ang);
         const rr_vec3 d = rr_qrot(euler_to_quat(0.f, alpha, beta), rr_v3(1.f, 0.f, 0.f));
         out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+        keys[i] = ((uint64_t)beam_morton_key(alpha, beta, radius) << 32) | (uint32_t)i;
     }
+    /* The draws are i.i.d., so their order carries no meaning in the reference; store them along a Morton curve over
+     * (alpha, beta) so that 32 consecutive samples (= one warp's rays) form a compact sub-bundle of the beam. */
+    std::sort(keys.begin(), keys.end());
+    std::vector<float> sorted((size_t)3 * n);
+    for (int i = 0; i < n; i++) {
+        const uint32_t src = (uint32_t)keys[i];
+        sorted[3 * i] = out[3 * src]; sorted[3 * i + 1] = out[3 * src + 1]; sorted[3 * i + 2] = out[3 * src + 2];
+    }
+    out.swap(sorted);
 }
 
 } // namespace
