@@ -276,7 +276,7 @@ def main():
             except Exception:
                 traffic = None
         cpu_fps, cpu_kind, cpu_cores, cpu_t = (None, "port", os.cpu_count() or 1, 0.0)
-        if world == 1 or True:
+        if args.cpu_frames > 0:
             cpu_fps, cpu_kind, cpu_cores, cpu_t = cpu_reference_run(scene, cfg, dirs, poses, args.cpu_frames, noise_seed)
         line = {
             "metric": "polar frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -290,7 +290,7 @@ def main():
             "casts_per_step": casts, "image_checksum": img_sum,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": POSES_PER_STEP * 28,
                     "d2h_bytes_per_step": POSES_PER_STEP * N_CELLS * N_ANGLES},
-            "gpu_launches": K,
+            "gpu_launches": 2 * K,            # rr_trace_kernel + rr_draw_kernel per step
             "wall_s_timed_region": wall,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

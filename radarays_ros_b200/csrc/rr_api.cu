@@ -13,8 +13,9 @@
 #include "rr_bvh.h"
 #include "rr_internal.h"
 
-extern "C" cudaError_t rr_launch_frame(const RRFrameParams* P, int grid, size_t smem, cudaStream_t st, int stats, int debug);
-extern "C" cudaError_t rr_frame_occupancy(int* blocks_per_sm, size_t smem);
+extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int grid, cudaStream_t st, int stats, int debug);
+extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug);
+extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
                                       const float* gs, const float* origins, const float* dirs, size_t n, float tmax,
                                       int32_t* face_ids, float* ranges, cudaStream_t st);
@@ -52,7 +53,8 @@ struct rr_ctx {
     /* scratch */
     int grid = 0; uint32_t wave_cap = 0, sig_cap = 0;
     float* d_wave_f32 = nullptr; double* d_wave_f64 = nullptr; uint32_t* d_wave_mat = nullptr;
-    int32_t* d_sig_cell = nullptr; float* d_sig_str = nullptr;
+    int32_t* d_sig_cell = nullptr; float* d_sig_str = nullptr; uint32_t* d_seg = nullptr; uint32_t* d_ipw = nullptr;
+    uint32_t n_chunks = 0, max_items = 0;          /* items (pose, azimuth) one launch pair can hold */
     uint32_t* d_work = nullptr; unsigned long long* d_counters = nullptr; int32_t* d_errflags = nullptr;
     /* host-buffer path staging */
     rr_pose* d_poses = nullptr; size_t d_poses_cap = 0;
@@ -288,7 +290,7 @@ void rr_destroy(rr_ctx* ctx)
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials);
     cudaFree(ctx->d_weights); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
     cudaFree(ctx->d_wave_f32); cudaFree(ctx->d_wave_f64); cudaFree(ctx->d_wave_mat);
-    cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str);
+    cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str); cudaFree(ctx->d_seg); cudaFree(ctx->d_ipw);
     cudaFree(ctx->d_work); cudaFree(ctx->d_counters); cudaFree(ctx->d_errflags);
     cudaFree(ctx->d_poses); cudaFree(ctx->d_out);
     if (ctx->h_poses) cudaFreeHost(ctx->h_poses);
@@ -476,32 +478,41 @@ static int ready(rr_ctx* ctx)
     return ensure_beam(ctx);
 }
 
-static int ensure_scratch(rr_ctx* ctx)
+/* Scratch: wave lists per resident trace warp; return buffers per task, for up to `want_items` items per launch pair
+ * (bounded to ~1.5 GB; larger batches are processed in several launch pairs by the callers). */
+static int ensure_scratch(rr_ctx* ctx, size_t want_items)
 {
-    const size_t smem = (size_t)ctx->cfg.n_cells * sizeof(float);
     int per_sm = 0;
-    CK(rr_frame_occupancy(&per_sm, smem));
-    if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "frame kernel does not fit on an SM (smem %zu)", smem);
+    CK(rr_trace_occupancy(&per_sm));
+    if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "trace kernel does not fit on an SM");
     const int grid = ctx->num_sms * per_sm;
     const uint32_t S = ctx->model.n_samples, Pn = ctx->model.n_reflections;
-    const uint32_t spw = (S + RR_WARPS - 1) / RR_WARPS;              /* samples per warp */
+    const uint32_t n_chunks = (S + RR_CHUNK - 1) / RR_CHUNK;
     uint32_t cap_w;
-    if (ctx->max_waves_user) cap_w = (ctx->max_waves_user + RR_WARPS - 1) / RR_WARPS;
-    else cap_w = spw * (1u << std::min<uint32_t>(Pn > 0 ? Pn - 1 : 0, 3));   /* room for 3 dielectric splits per path */
-    cap_w = std::max<uint32_t>(cap_w, spw);
+    if (ctx->max_waves_user) cap_w = (ctx->max_waves_user + n_chunks - 1) / n_chunks;
+    else cap_w = RR_CHUNK * (1u << std::min<uint32_t>(Pn > 0 ? Pn - 1 : 0, 3));   /* room for 3 dielectric splits per path */
+    cap_w = std::max<uint32_t>(cap_w, RR_CHUNK);
     cap_w = (cap_w + 31u) & ~31u;
     const uint32_t scap_w = 2u * cap_w * std::max<uint32_t>(1, std::min<uint32_t>(Pn, 6));
-    if (grid != ctx->grid || cap_w != ctx->wave_cap || scap_w != ctx->sig_cap) {
+    const size_t per_item = (size_t)n_chunks * ((size_t)scap_w * 8 + RR_MAX_PASSES * 4) + RR_MAX_PASSES * 4;
+    size_t max_items = std::max<size_t>(RR_N_ANGLES, (size_t)1536 * 1024 * 1024 / per_item);
+    max_items = std::min<size_t>(max_items, std::max<size_t>(want_items, RR_N_ANGLES));
+    if (grid != ctx->grid || cap_w != ctx->wave_cap || scap_w != ctx->sig_cap || n_chunks != ctx->n_chunks || max_items > ctx->max_items) {
         cudaFree(ctx->d_wave_f32); cudaFree(ctx->d_wave_f64); cudaFree(ctx->d_wave_mat); cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str);
+        cudaFree(ctx->d_seg); cudaFree(ctx->d_ipw);
         ctx->d_wave_f32 = nullptr; ctx->d_wave_f64 = nullptr; ctx->d_wave_mat = nullptr; ctx->d_sig_cell = nullptr; ctx->d_sig_str = nullptr;
-        ctx->grid = 0;
-        const size_t warps = (size_t)grid * RR_WARPS;
+        ctx->d_seg = nullptr; ctx->d_ipw = nullptr;
+        ctx->grid = 0; ctx->max_items = 0;
+        const size_t warps = (size_t)grid * (RR_TRACE_BLOCK / 32);
+        const size_t tasks = max_items * n_chunks;
         CK(cudaMalloc((void**)&ctx->d_wave_f32, warps * 2 * 6 * cap_w * sizeof(float)));
         CK(cudaMalloc((void**)&ctx->d_wave_f64, warps * 2 * 2 * cap_w * sizeof(double)));
         CK(cudaMalloc((void**)&ctx->d_wave_mat, warps * 2 * cap_w * sizeof(uint32_t)));
-        CK(cudaMalloc((void**)&ctx->d_sig_cell, warps * scap_w * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&ctx->d_sig_str, warps * scap_w * sizeof(float)));
-        ctx->grid = grid; ctx->wave_cap = cap_w; ctx->sig_cap = scap_w;
+        CK(cudaMalloc((void**)&ctx->d_sig_cell, tasks * scap_w * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&ctx->d_sig_str, tasks * scap_w * sizeof(float)));
+        CK(cudaMalloc((void**)&ctx->d_seg, tasks * RR_MAX_PASSES * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&ctx->d_ipw, max_items * RR_MAX_PASSES * sizeof(uint32_t)));
+        ctx->grid = grid; ctx->wave_cap = cap_w; ctx->sig_cap = scap_w; ctx->n_chunks = n_chunks; ctx->max_items = (uint32_t)max_items;
     }
     return RR_OK;
 }
@@ -529,17 +540,37 @@ static void fill_params(rr_ctx* ctx, RRFrameParams& P)
     P.noise_seed = ctx->noise_seed;
     P.wave_f32 = ctx->d_wave_f32; P.wave_f64 = ctx->d_wave_f64; P.wave_mat = ctx->d_wave_mat;
     P.sig_cell = ctx->d_sig_cell; P.sig_strength = ctx->d_sig_str; P.wave_cap_w = ctx->wave_cap; P.sig_cap_w = ctx->sig_cap;
+    P.seg_counts = ctx->d_seg; P.item_pass_waves = ctx->d_ipw; P.n_chunks = (int32_t)ctx->n_chunks;
     P.work_counter = ctx->d_work; P.counters = ctx->d_counters; P.error_flags = ctx->d_errflags;
 }
 
+/* One launch pair (trace + draw) per sub-batch of poses; counters accumulate over the whole call. */
 static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, int debug)
 {
-    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(uint32_t), st));
     CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->d_errflags, 0, 4 * sizeof(int32_t), st));
-    const uint32_t items = (uint32_t)P.n_poses * (uint32_t)P.az_count;
-    const int grid = (int)std::min<uint32_t>((uint32_t)ctx->grid, std::max<uint32_t>(items, 1));
-    CK(rr_launch_frame(&P, grid, (size_t)P.n_cells * sizeof(float), st, stats, debug));
+    const int n_total = P.n_poses;
+    const int poses_per_launch = std::max<int>(1, (int)(ctx->max_items / (uint32_t)P.az_count));
+    const rr_pose* poses0 = P.poses;
+    uint8_t* out0 = P.out;
+    const uint64_t frame0 = P.frame_id0;
+    const size_t out_stride = P.column_major ? (size_t)P.az_count * P.n_cells : (size_t)P.n_cells * RR_N_ANGLES;
+    for (int first = 0; first < n_total; first += poses_per_launch) {
+        const int n = std::min(poses_per_launch, n_total - first);
+        P.n_poses = n;
+        P.poses = poses0 + (size_t)first * (P.pose_per_azimuth ? RR_N_ANGLES : 1);
+        P.out = out0 + (size_t)first * out_stride;
+        P.frame_id0 = frame0 + (uint64_t)first;
+        const uint32_t items = (uint32_t)n * (uint32_t)P.az_count;
+        const uint32_t tasks = items * (uint32_t)P.n_chunks;
+        CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(ctx->d_ipw, 0, (size_t)items * RR_MAX_PASSES * sizeof(uint32_t), st));
+        const uint32_t warps_per_cta = RR_TRACE_BLOCK / 32;
+        const int grid = (int)std::min<uint32_t>((uint32_t)ctx->grid, (tasks + warps_per_cta - 1) / warps_per_cta);
+        CK(rr_launch_trace(&P, std::max(grid, 1), st, stats, debug));
+        CK(rr_launch_draw(&P, (int)items, (size_t)P.n_cells * sizeof(float), st, debug));
+    }
+    P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0;
     return RR_OK;
 }
 
@@ -555,7 +586,7 @@ static int collect(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
     s.kernel_ms = kernel_ms; s.bvh_build_ms = ctx->bvh_build_ms; s.overflow = flags[0];
     if (stats) *stats = s;
     if (flags[1]) return fail(ctx, RR_ERR_OUT_OF_RANGE, "a hit face carries an object id >= n_objects");
-    if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave/signal list overflow (cap %u waves per warp = %u per azimuth); raise rr_set_max_waves_per_azimuth", ctx->wave_cap, ctx->wave_cap * RR_WARPS);
+    if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave/signal list overflow (cap %u waves per %d-sample chunk = %u per azimuth); raise rr_set_max_waves_per_azimuth", ctx->wave_cap, RR_CHUNK, ctx->wave_cap * ctx->n_chunks);
     return RR_OK;
 }
 
@@ -565,7 +596,7 @@ static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int
     int rc = ready(ctx);
     if (rc) return rc;
     if (!poses || !out_polar || n_frames == 0) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "simulate: NULL buffers or zero poses");
-    if ((rc = ensure_scratch(ctx))) return rc;
+    if ((rc = ensure_scratch(ctx, n_frames * RR_N_ANGLES))) return rc;
     const size_t n_pose_structs = n_frames * (per_az ? RR_N_ANGLES : 1);
     const size_t img = (size_t)ctx->cfg.n_cells * RR_N_ANGLES;
     CK(regrow(&ctx->d_poses, &ctx->d_poses_cap, n_pose_structs));
@@ -616,7 +647,7 @@ int rr_simulate_device(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64
     if (!d_Tsm || !d_out_polar || n_poses == 0) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_device: NULL buffers or zero poses");
     if (azimuth_begin < 0 || azimuth_count < 1 || azimuth_begin + azimuth_count > RR_N_ANGLES)
         return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_device: azimuth shard [%d,%d) outside [0,400)", azimuth_begin, azimuth_begin + azimuth_count);
-    if ((rc = ensure_scratch(ctx))) return rc;
+    if ((rc = ensure_scratch(ctx, n_poses * (size_t)azimuth_count))) return rc;
     RRFrameParams P;
     fill_params(ctx, P);
     P.poses = d_Tsm; P.n_poses = (int)n_poses; P.pose_per_azimuth = pose_per_azimuth ? 1 : 0;
@@ -641,22 +672,23 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
     int rc = ready(ctx);
     if (rc) return rc;
     if (!Tsm) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_debug_trace: NULL pose");
-    if ((rc = ensure_scratch(ctx))) return rc;
+    if ((rc = ensure_scratch(ctx, RR_N_ANGLES))) return rc;
     const uint32_t Pn = std::max<uint32_t>(1, ctx->model.n_reflections);
-    const uint32_t ccap = ctx->wave_cap * Pn, scap = ctx->sig_cap;          /* per warp */
+    const uint32_t ccap = ctx->wave_cap * Pn, scap = ctx->sig_cap;          /* per task */
+    const uint32_t n_chunks = ctx->n_chunks;
+    const size_t n_tasks = (size_t)RR_N_ANGLES * n_chunks;
     const int C = ctx->cfg.n_cells;
-    const size_t n_cnt = (size_t)RR_N_ANGLES * RR_MAX_PASSES * RR_WARPS * 2;
     rr_cast_record* d_casts = nullptr; rr_signal_record* d_sigs = nullptr; uint32_t* d_cnt = nullptr; float* d_cols = nullptr;
     rr_pose* d_pose = nullptr; uint8_t* d_img = nullptr;
     auto cleanup = [&]() { cudaFree(d_casts); cudaFree(d_sigs); cudaFree(d_cnt); cudaFree(d_cols); cudaFree(d_pose); cudaFree(d_img); };
 #define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
-    CKD(cudaMalloc((void**)&d_casts, (size_t)RR_N_ANGLES * RR_WARPS * ccap * sizeof(rr_cast_record)));
-    CKD(cudaMalloc((void**)&d_sigs, (size_t)RR_N_ANGLES * RR_WARPS * scap * sizeof(rr_signal_record)));
-    CKD(cudaMalloc((void**)&d_cnt, n_cnt * sizeof(uint32_t)));
+    CKD(cudaMalloc((void**)&d_casts, n_tasks * ccap * sizeof(rr_cast_record)));
+    CKD(cudaMalloc((void**)&d_sigs, n_tasks * scap * sizeof(rr_signal_record)));
+    CKD(cudaMalloc((void**)&d_cnt, n_tasks * RR_MAX_PASSES * sizeof(uint32_t)));
     CKD(cudaMalloc((void**)&d_cols, (size_t)RR_N_ANGLES * C * sizeof(float)));
     CKD(cudaMalloc((void**)&d_pose, sizeof(rr_pose)));
     CKD(cudaMalloc((void**)&d_img, (size_t)C * RR_N_ANGLES));
-    CKD(cudaMemset(d_cnt, 0, n_cnt * sizeof(uint32_t)));
+    CKD(cudaMemset(d_cnt, 0, n_tasks * RR_MAX_PASSES * sizeof(uint32_t)));
     CKD(cudaMemcpy(d_pose, Tsm, sizeof(rr_pose), cudaMemcpyHostToDevice));
     RRFrameParams P;
     fill_params(ctx, P);
@@ -666,24 +698,27 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
     P.dbg_cast_cap_w = ccap; P.dbg_sig_cap_w = scap;
     if ((rc = enqueue(ctx, P, ctx->stream, 1, 1))) { cleanup(); return rc; }
     CKD(cudaStreamSynchronize(ctx->stream));
-    /* re-assemble the reference's list order: for azimuth, for pass, for warp: that warp's (pass) segment */
-    std::vector<uint32_t> cnt(n_cnt);
-    std::vector<rr_cast_record> hc((size_t)RR_N_ANGLES * RR_WARPS * ccap);
-    std::vector<rr_signal_record> hs((size_t)RR_N_ANGLES * RR_WARPS * scap);
-    CKD(cudaMemcpy(cnt.data(), d_cnt, n_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    /* re-assemble the reference's list order: for azimuth, for pass, for chunk: that chunk's (pass) segment */
+    std::vector<uint32_t> ccnt(n_tasks * RR_MAX_PASSES), scnt(n_tasks * RR_MAX_PASSES);
+    std::vector<rr_cast_record> hc(n_tasks * ccap);
+    std::vector<rr_signal_record> hs(n_tasks * scap);
+    CKD(cudaMemcpy(ccnt.data(), d_cnt, ccnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(scnt.data(), ctx->d_seg, scnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CKD(cudaMemcpy(hc.data(), d_casts, hc.size() * sizeof(rr_cast_record), cudaMemcpyDeviceToHost));
     CKD(cudaMemcpy(hs.data(), d_sigs, hs.size() * sizeof(rr_signal_record), cudaMemcpyDeviceToHost));
     size_t nc = 0, ns = 0;
+    std::vector<uint32_t> coff(n_chunks), soff(n_chunks);
     for (int a = 0; a < RR_N_ANGLES; a++) {
-        uint32_t coff[RR_WARPS] = {0}, soff[RR_WARPS] = {0};
+        std::fill(coff.begin(), coff.end(), 0u); std::fill(soff.begin(), soff.end(), 0u);
         for (uint32_t p = 0; p < ctx->model.n_reflections; p++) {
-            for (int w = 0; w < RR_WARPS; w++) {
-                const uint32_t* c2 = &cnt[(((size_t)a * RR_MAX_PASSES + p) * RR_WARPS + w) * 2];
-                for (uint32_t k = 0; k < c2[0]; k++, nc++)
-                    if (casts && nc < cast_capacity && coff[w] + k < ccap) casts[nc] = hc[((size_t)a * RR_WARPS + w) * ccap + coff[w] + k];
-                for (uint32_t k = 0; k < c2[1]; k++, ns++)
-                    if (signals && ns < signal_capacity && soff[w] + k < scap) signals[ns] = hs[((size_t)a * RR_WARPS + w) * scap + soff[w] + k];
-                coff[w] += c2[0]; soff[w] += c2[1];
+            for (uint32_t w = 0; w < n_chunks; w++) {
+                const size_t task = (size_t)a * n_chunks + w;
+                const uint32_t c2 = ccnt[task * RR_MAX_PASSES + p], s2 = scnt[task * RR_MAX_PASSES + p];
+                for (uint32_t k = 0; k < c2; k++, nc++)
+                    if (casts && nc < cast_capacity && coff[w] + k < ccap) casts[nc] = hc[task * ccap + coff[w] + k];
+                for (uint32_t k = 0; k < s2; k++, ns++)
+                    if (signals && ns < signal_capacity && soff[w] + k < scap) signals[ns] = hs[task * scap + soff[w] + k];
+                coff[w] += c2; soff[w] += s2;
             }
         }
     }

@@ -42,6 +42,8 @@ struct RRBuildNode {
 #define RR_MAX_DENOISE 256
 #define RR_BLOCK 256
 #define RR_WARPS (RR_BLOCK / 32)
+#define RR_TRACE_BLOCK 128       /* trace kernel: 4 independent warps per CTA */
+#define RR_CHUNK 32              /* beam samples per trace task (= one warp) */
 #define RR_MAX_PASSES 20         /* cfg/RadarModel.cfg:27 n_reflections <= 20 */
 
 struct RRFrameParams {
@@ -74,21 +76,25 @@ struct RRFrameParams {
     /* output */
     uint8_t* out;                  /* row-major [pose][cell][400] or column-major [pose][az-az_begin][cell] */
     int32_t column_major;
-    /* per-warp scratch (8 warps per CTA; SoA so that lanes access consecutive words) */
-    float* wave_f32;               /* [cta][warp][2 lists][6 comps][wave_cap_w] orig.xyz dir.xyz */
-    double* wave_f64;              /* [cta][warp][2 lists][2 comps][wave_cap_w] energy, time */
-    uint32_t* wave_mat;            /* [cta][warp][2 lists][wave_cap_w] material id */
-    int32_t* sig_cell;             /* [cta][warp][sig_cap_w] returns in generation order */
-    float* sig_strength;           /* [cta][warp][sig_cap_w] */
+    /* per-resident-warp scratch of the trace kernel (SoA so that lanes access consecutive words) */
+    float* wave_f32;               /* [warp][2 lists][6 comps][wave_cap_w] orig.xyz dir.xyz */
+    double* wave_f64;              /* [warp][2 lists][2 comps][wave_cap_w] energy, time */
+    uint32_t* wave_mat;            /* [warp][2 lists][wave_cap_w] material id */
+    /* per-task output of the trace kernel; task = (pose, azimuth, chunk of RR_CHUNK samples) */
+    int32_t* sig_cell;             /* [task][sig_cap_w] returns in generation order (pass 0 first) */
+    float* sig_strength;           /* [task][sig_cap_w] */
+    uint32_t* seg_counts;          /* [task][RR_MAX_PASSES] returns emitted in each pass */
+    uint32_t* item_pass_waves;     /* [item][RR_MAX_PASSES] waves traced per pass (stats: max list length) */
     uint32_t wave_cap_w, sig_cap_w;
+    int32_t n_chunks;              /* ceil(n_samples / RR_CHUNK) */
     /* control + counters */
     uint32_t* work_counter;
     unsigned long long* counters;  /* [0] casts [1] hits [2] signals [3] nodes [4] tris [5] max_waves */
     int32_t* error_flags;          /* [0] wave overflow [1] object/material id out of range */
     /* debug (rr_debug_trace) */
-    rr_cast_record* dbg_casts;     /* [az][warp][dbg_cast_cap_w], per warp in (pass, list) order */
-    rr_signal_record* dbg_signals; /* [az][warp][dbg_sig_cap_w] */
-    uint32_t* dbg_counts;          /* [az][RR_MAX_PASSES][warp][2] = (casts, signals) of that (pass, warp) segment */
+    rr_cast_record* dbg_casts;     /* [task][dbg_cast_cap_w], per task in (pass, list) order */
+    rr_signal_record* dbg_signals; /* [task][dbg_sig_cap_w] */
+    uint32_t* dbg_counts;          /* [task][RR_MAX_PASSES] casts of that (task, pass) segment */
     float* dbg_columns;            /* [az][cell] */
     uint32_t dbg_cast_cap_w, dbg_sig_cap_w;
 };

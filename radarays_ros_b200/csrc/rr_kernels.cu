@@ -1,11 +1,12 @@
-/* rr_kernels.cu — sm_100a kernels of the RadaRays hot path.
+/* rr_kernels.cu — sm_100a kernels of the RadaRays hot path (RadarCPU::simulate, RadarCPU.cpp:30-564).
  *
- * rr_frame_kernel fuses, per (pose, azimuth) work item owned by one persistent CTA:
+ * rr_trace_kernel (persistent, barrier-free, one WARP per 32-sample chunk task):
  *   beam bundle generation      (RadarCPU.cpp:184-209, radar_algorithms.cpp:150-169)
  *   closest-hit traversal       (Rmagine/Embree call at RadarCPU.cpp:236) over the 32-byte quantised BVH
  *   move + Snell/Fresnel + BRDF (radar_types.h:108-120, radar_algorithms.h:55-139,168-187, RadarCPU.cpp:243-371)
- *   pruning + ordered respawn   (RadarCPU.cpp:288-290,364-389) via block scans (keeps the reference's list order)
- *   range-bin accumulation      (RadarCPU.cpp:402-450) into a shared-memory column, in reference order
+ *   pruning + ordered respawn   (RadarCPU.cpp:288-290,364-389) via ballot/popc compaction (keeps the reference's list order)
+ * rr_draw_kernel (one CTA per (pose, azimuth)):
+ *   range-bin accumulation      (RadarCPU.cpp:402-450) into a shared-memory column, in reference order, no atomics
  *   energy_max / ambient noise / normalise / mono8 (RadarCPU.cpp:453-542)
  * The arithmetic is written independently of oracle/rr_oracle.cpp; only the elementary primitives of
  * rr_detmath.h are shared. Compile with --fmad=false: every fused multiply-add below is explicit.
@@ -14,7 +15,7 @@
 
 #define RR_FULL 0xffffffffu
 #ifndef RR_MIN_BLOCKS
-#define RR_MIN_BLOCKS 4            /* resident CTAs per SM the register allocation is tuned for */
+#define RR_MIN_BLOCKS 10           /* resident 128-thread trace CTAs per SM the register allocation is tuned for */
 #endif
 
 /* Wave state. Quirk kept on purpose: the reference never updates DirectedWave::velocity on the waves it pushes
@@ -178,57 +179,46 @@ __device__ __forceinline__ uint8_t rr_to_u8(float v)
 }
 
 /* ------------------------------------------------------------------------------------------------
- * the fused frame kernel
+ * Kernel 1/2: rr_trace_kernel — beam rays -> multi-bounce closest hit -> Snell/Fresnel + BRDF -> returns.
  *
- * One persistent CTA owns one (pose, azimuth) work item at a time. Inside it the 8 warps are DECOUPLED while
- * tracing: warp w owns the contiguous sample chunk [w*spw, (w+1)*spw) and walks its wave tree through all passes
- * on its own (ballot/popc compaction into per-warp ping-pong lists, no block barrier). The reference's list order
- * (RadarCPU.cpp:243,290,322,369: pass-major, parents in order, reflection before refraction) is kept because by
- * induction every warp's waves form one contiguous run of each pass's list: the canonical order is
- * "for pass: for warp: that warp's (pass) segment", which the draw phase replays from a segment table.
+ * Persistent, barrier-free: every WARP is an independent worker pulling (pose, azimuth, chunk) tasks from a global
+ * counter; a chunk is 32 consecutive beam samples and the warp walks that chunk's wave tree through all passes on
+ * its own (ballot/popc compaction into the warp's ping-pong lists, no block barrier, no shared memory). The
+ * reference's list order (RadarCPU.cpp:243,290,322,369: pass-major, parents in order, reflection before refraction)
+ * is kept because by induction every chunk's waves form one contiguous run of each pass's list: the canonical order is
+ * "for pass: for chunk: that chunk's (pass) segment", which rr_draw_kernel replays from the per-task segment counts.
  * ---------------------------------------------------------------------------------------------- */
 template <bool STATS, bool DEBUG>
-__global__ void __launch_bounds__(RR_BLOCK, RR_MIN_BLOCKS) rr_frame_kernel(const RRFrameParams P)
+__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel(const RRFrameParams P)
 {
-    extern __shared__ float s_col[];                     /* n_cells floats: this azimuth's range column */
-    __shared__ float s_weights[RR_MAX_DENOISE];
-    __shared__ unsigned char s_perm[256];
-    __shared__ uint32_t s_seg_start[RR_MAX_PASSES][RR_WARPS];   /* per-(pass, warp) run inside the warp's signal buffer */
-    __shared__ uint32_t s_seg_count[RR_MAX_PASSES][RR_WARPS];
-    __shared__ uint32_t s_pass_waves[RR_MAX_PASSES];
-    __shared__ float s_red[RR_WARPS];
-    __shared__ uint32_t s_item, s_hits;
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? P.denoise_weights[i] : 0.f;
-    for (int i = tid; i < 256; i += RR_BLOCK) s_perm[i] = c_perlin_perm[i];
-
     const uint32_t cap = P.wave_cap_w, scap = P.sig_cap_w;
-    const size_t wslot = (size_t)blockIdx.x * RR_WARPS + wid;
+    const size_t wslot = (size_t)blockIdx.x * (RR_TRACE_BLOCK / 32) + warp_in_block;
     float* wf = P.wave_f32 + wslot * 2 * 6 * cap;
     double* wd = P.wave_f64 + wslot * 2 * 2 * cap;
     uint32_t* wm = P.wave_mat + wslot * 2 * cap;
-    int32_t* sg_cell = P.sig_cell + wslot * scap;
-    float* sg_str = P.sig_strength + wslot * scap;
-    const int C = P.n_cells;
     const int n_passes = P.n_passes;
-    const uint32_t total_items = (uint32_t)P.n_poses * (uint32_t)P.az_count;
+    const uint32_t n_chunks = (uint32_t)P.n_chunks;
+    const uint32_t total_tasks = (uint32_t)P.n_poses * (uint32_t)P.az_count * n_chunks;
     const float go[3] = {P.grid_origin[0], P.grid_origin[1], P.grid_origin[2]};
     const float gs[3] = {P.grid_scale[0], P.grid_scale[1], P.grid_scale[2]};
-    const uint32_t spw = ((uint32_t)P.n_samples + RR_WARPS - 1) / RR_WARPS;      /* samples per warp */
-    const uint32_t s_begin = min((uint32_t)P.n_samples, (uint32_t)wid * spw);
-    const uint32_t s_count = min((uint32_t)P.n_samples, s_begin + spw) - s_begin;
+    unsigned stat_nodes = 0, stat_tris = 0;
 
     while (true) {
-        __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(P.work_counter, 1u); s_hits = 0; }
-        if (tid < RR_MAX_PASSES) s_pass_waves[tid] = 0;
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= total_items) break;
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(P.work_counter, 1u);
+        task = __shfl_sync(RR_FULL, task, 0);
+        if (task >= total_tasks) break;
+        const uint32_t item = task / n_chunks, chunk = task % n_chunks;
         const int pose_i = (int)(item / (uint32_t)P.az_count);
         const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
+        const uint32_t s_begin = chunk * 32u;
+        const uint32_t s_count = min((uint32_t)P.n_samples - s_begin, 32u);
+        int32_t* sg_cell = P.sig_cell + (size_t)task * scap;
+        float* sg_str = P.sig_strength + (size_t)task * scap;
+        uint32_t* seg = P.seg_counts + (size_t)task * RR_MAX_PASSES;
 
         /* Tam = Tsm * Tas (RadarCPU.cpp:201-206); Tas.t = 0 */
         const rr_pose ps = P.poses[P.pose_per_azimuth ? (pose_i * RR_N_ANGLES + az) : pose_i];
@@ -239,13 +229,9 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_MIN_BLOCKS) rr_frame_kernel(const
         const rr_quat Rinv = rr_qinv(R);
         const rr_vec3 T = rr_add(rr_qrot(Rsm, rr_v3(0.f, 0.f, 0.f)), rr_v3(ps.tx, ps.ty, ps.tz));
 
-        for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
-
-        /* ================= trace: this warp's samples through all passes, no block barrier ================= */
         uint32_t n_cur = s_count;
         int cur = 0;
         uint32_t sig_off = 0, warp_hits = 0, warp_casts = 0;
-        unsigned stat_nodes = 0, stat_tris = 0;
 
         for (int pass = 0; pass < n_passes; pass++) {
             const bool last_pass = (pass == n_passes - 1);
@@ -430,7 +416,7 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_MIN_BLOCKS) rr_frame_kernel(const
                     if (so < scap) { sg_cell[so] = sig_cell0; sg_str[so] = sig_s0; }
                     if (n_sig > 1 && so + 1 < scap) { sg_cell[so + 1] = sig_cell1; sg_str[so + 1] = sig_s1; }
                     if (DEBUG) {
-                        rr_signal_record* ds = P.dbg_signals + ((size_t)az * RR_WARPS + wid) * P.dbg_sig_cap_w;
+                        rr_signal_record* ds = P.dbg_signals + (size_t)task * P.dbg_sig_cap_w;
                         if (so < P.dbg_sig_cap_w) {
                             rr_signal_record r; r.azimuth = az; r.cell = sig_cell0; r.strength = sig_s0; r.time = sig_t0;
                             ds[so] = r;
@@ -444,19 +430,15 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_MIN_BLOCKS) rr_frame_kernel(const
                 if (DEBUG && active && warp_casts + i < P.dbg_cast_cap_w) {
                     rr_cast_record r; r.azimuth = az; r.pass = pass; r.face_id = hit ? face : -1;
                     r.range = hit ? range : 0.f; r.energy = dbg_energy; r.n_children = (int)n_child;
-                    P.dbg_casts[((size_t)az * RR_WARPS + wid) * P.dbg_cast_cap_w + warp_casts + i] = r;
+                    P.dbg_casts[(size_t)task * P.dbg_cast_cap_w + warp_casts + i] = r;
                 }
                 next_n += __popc(m0) + __popc(m1);
                 sig_off += __popc(ms0) + __popc(ms1);
             }
             if (lane == 0) {
-                s_seg_start[pass][wid] = seg_start;
-                s_seg_count[pass][wid] = min(sig_off, scap) - min(seg_start, scap);
-                atomicAdd(&s_pass_waves[pass], n_cur);
-                if (DEBUG) {
-                    uint32_t* dc = P.dbg_counts + (((size_t)az * RR_MAX_PASSES + pass) * RR_WARPS + wid) * 2;
-                    dc[0] = n_cur; dc[1] = s_seg_count[pass][wid];
-                }
+                seg[pass] = min(sig_off, scap) - min(seg_start, scap);
+                atomicAdd(&P.item_pass_waves[(size_t)item * RR_MAX_PASSES + pass], n_cur);
+                if (DEBUG) P.dbg_counts[(size_t)task * RR_MAX_PASSES + pass] = n_cur;
             }
             warp_casts += n_cur;
             if ((next_n > cap || sig_off > scap) && lane == 0) atomicExch(&P.error_flags[0], 1);
@@ -464,133 +446,157 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_MIN_BLOCKS) rr_frame_kernel(const
             cur ^= 1;
             __syncwarp();                                /* children written by other lanes are read next pass */
         }
-        if (lane == 0) atomicAdd(&s_hits, warp_hits);
-        __syncthreads();
+        if (lane == 0) {
+            atomicAdd(&P.counters[0], (unsigned long long)warp_casts);
+            atomicAdd(&P.counters[1], (unsigned long long)warp_hits);
+            atomicAdd(&P.counters[2], (unsigned long long)min(sig_off, scap));
+        }
+    }
+    if (STATS) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            stat_nodes += __shfl_xor_sync(RR_FULL, stat_nodes, off);
+            stat_tris += __shfl_xor_sync(RR_FULL, stat_tris, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.counters[3], (unsigned long long)stat_nodes);
+            atomicAdd(&P.counters[4], (unsigned long long)stat_tris);
+        }
+    }
+}
 
-        /* ================= signals -> column (RadarCPU.cpp:402-450), in the reference's order =================
-         * Bins are dealt to the warps in 32-bin granules, round-robin (granule G belongs to warp G % 8, bin g to
-         * lane g % 32), so a bin always has the same owner thread and sees its additions in program order = list
-         * order; a W <= 200 wide splat touches at most one granule per warp. Every warp replays the segment table;
-         * 32 signals are tested at once and only the ones touching this warp's granules are applied. */
-        float m = 0.0f;
-        {
-            const int W = P.denoise_on ? P.denoise_width : 1;
-            const int mode = P.denoise_on ? P.denoise_mode : 0;
-            const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
-            for (int pass = 0; pass < n_passes; pass++) {
-                for (int sw = 0; sw < RR_WARPS; sw++) {
-                    const uint32_t cnt = s_seg_count[pass][sw];
-                    if (cnt == 0) continue;
-                    const size_t soff = ((size_t)blockIdx.x * RR_WARPS + sw) * scap + s_seg_start[pass][sw];
-                    const int32_t* pc = P.sig_cell + soff;
-                    const float* pst = P.sig_strength + soff;
-                    for (uint32_t base = 0; base < cnt; base += 32) {
-                        const bool valid = base + lane < cnt;
-                        const int cell = valid ? pc[base + lane] : 0;
-                        const float str = valid ? pst[base + lane] : 0.f;
-                        /* cell < C (:414); very negative cells (time = -inf/NaN) can not reach a bin */
-                        bool rel = valid && (cell < C) && (cell > -RR_MAX_DENOISE - 1);
-                        const int start = cell - mode;
-                        const int gs0 = start >> 5, ge0 = (start + W - 1) >> 5;
-                        rel = rel && (gs0 + ((wid - gs0) & (RR_WARPS - 1)) <= ge0);
-                        uint32_t mask = __ballot_sync(RR_FULL, rel);
-                        while (mask) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const int st = __shfl_sync(RR_FULL, start, j);
-                            const float sv = __shfl_sync(RR_FULL, str, j);
-                            const int g0 = st >> 5;
-                            const int g = ((g0 + ((wid - g0) & (RR_WARPS - 1))) << 5) + lane;
-                            if (g >= max(st, lo_bin) && g < min(st + W, C)) {
-                                float v;
-                                if (P.denoise_on) {
-                                    v = (float)((double)s_col[g] + (double)sv * (double)s_weights[g - st]);
-                                } else {
-                                    const float old = s_col[g];
-                                    v = (old < sv) ? sv : old;                 /* std::max(old, strength), :439 */
-                                }
-                                s_col[g] = v;
-                                if (v > m) m = v;                              /* running max_val, :428-431 */
+/* ------------------------------------------------------------------------------------------------
+ * Kernel 2/2: rr_draw_kernel — returns -> range column (RadarCPU.cpp:402-450) -> energy_max, ambient noise,
+ * normalise, mono8 (RadarCPU.cpp:453-542). One CTA per (pose, azimuth); the column lives in shared memory.
+ *
+ * Accumulation is in the reference's order WITHOUT atomics: bins are dealt to the warps in 32-bin granules,
+ * round-robin (granule G belongs to warp G % 8, bin g to lane g % 32), so a bin always has the same owner thread and
+ * sees its additions in program order = list order; a W <= 200 wide splat touches at most one granule per warp.
+ * Every warp replays the (pass, chunk) segments; 32 returns are tested at once (ballot) and only the ones touching
+ * this warp's granules are applied. The float column is therefore bit-identical to the sequential reference loop.
+ * ---------------------------------------------------------------------------------------------- */
+template <bool DEBUG>
+__global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P)
+{
+    extern __shared__ float s_col[];                     /* n_cells floats: this azimuth's range column */
+    __shared__ float s_weights[RR_MAX_DENOISE];
+    __shared__ unsigned char s_perm[256];
+    __shared__ float s_red[RR_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t item = blockIdx.x;
+    const int pose_i = (int)(item / (uint32_t)P.az_count);
+    const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
+    const int C = P.n_cells;
+    const int n_passes = P.n_passes;
+    const uint32_t n_chunks = (uint32_t)P.n_chunks, scap = P.sig_cap_w;
+    for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? P.denoise_weights[i] : 0.f;
+    for (int i = tid; i < 256; i += RR_BLOCK) s_perm[i] = c_perlin_perm[i];
+    for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
+    __syncthreads();
+
+    float m = 0.0f;
+    {
+        const int W = P.denoise_on ? P.denoise_width : 1;
+        const int mode = P.denoise_on ? P.denoise_mode : 0;
+        const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
+        for (int pass = 0; pass < n_passes; pass++) {
+            for (uint32_t ch = 0; ch < n_chunks; ch++) {
+                const size_t task = (size_t)item * n_chunks + ch;
+                const uint32_t* seg = P.seg_counts + task * RR_MAX_PASSES;
+                const uint32_t cnt = seg[pass];
+                if (cnt == 0) continue;
+                uint32_t start_off = 0;
+                for (int p2 = 0; p2 < pass; p2++) start_off += seg[p2];
+                const int32_t* pc = P.sig_cell + task * scap + start_off;
+                const float* pst = P.sig_strength + task * scap + start_off;
+                for (uint32_t base = 0; base < cnt; base += 32) {
+                    const bool valid = base + lane < cnt;
+                    const int cell = valid ? pc[base + lane] : 0;
+                    const float str = valid ? pst[base + lane] : 0.f;
+                    /* cell < C (:414); very negative cells (time = -inf/NaN) can not reach a bin */
+                    bool rel = valid && (cell < C) && (cell > -RR_MAX_DENOISE - 1);
+                    const int start = cell - mode;
+                    const int gs0 = start >> 5, ge0 = (start + W - 1) >> 5;
+                    rel = rel && (gs0 + ((wid - gs0) & (RR_WARPS - 1)) <= ge0);
+                    uint32_t mask = __ballot_sync(RR_FULL, rel);
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int st = __shfl_sync(RR_FULL, start, j);
+                        const float sv = __shfl_sync(RR_FULL, str, j);
+                        const int g0 = st >> 5;
+                        const int g = ((g0 + ((wid - g0) & (RR_WARPS - 1))) << 5) + lane;
+                        if (g >= max(st, lo_bin) && g < min(st + W, C)) {
+                            float v;
+                            if (P.denoise_on) {
+                                v = (float)((double)s_col[g] + (double)sv * (double)s_weights[g - st]);
+                            } else {
+                                const float old = s_col[g];
+                                v = (old < sv) ? sv : old;                 /* std::max(old, strength), :439 */
                             }
+                            s_col[g] = v;
+                            if (v > m) m = v;                              /* running max_val, :428-431 */
                         }
                     }
                 }
             }
         }
+    }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) { const float o2 = __shfl_xor_sync(RR_FULL, m, off); if (o2 > m) m = o2; }
-        if (lane == 0) s_red[wid] = m;
-        __syncthreads();
-        float max_val = 0.0f;
+    for (int off = 16; off > 0; off >>= 1) { const float o2 = __shfl_xor_sync(RR_FULL, m, off); if (o2 > m) m = o2; }
+    if (lane == 0) s_red[wid] = m;
+    __syncthreads();
+    float max_val = 0.0f;
 #pragma unroll
-        for (int k = 0; k < RR_WARPS; k++) if (s_red[k] > max_val) max_val = s_red[k];
+    for (int k = 0; k < RR_WARPS; k++) if (s_red[k] > max_val) max_val = s_red[k];
 
-        /* ================= energy_max, ambient noise, normalise, mono8 (RadarCPU.cpp:453-542) ================= */
-        const int col = (P.scroll_image + az) % RR_N_ANGLES;
-        const uint64_t frame_id = P.frame_id0 + (uint64_t)pose_i;
-        const float signal_amp = max_val - 0.0f;
-        const float noise_at_0 = (float)((double)signal_amp * P.noise_at_signal_0);
-        const float noise_at_1 = (float)((double)signal_amp * P.noise_at_signal_1);
-        const float ne_max = (float)((double)max_val * P.noise_energy_max);
-        const float ne_min = (float)((double)max_val * P.noise_energy_min);
-        const float e_loss = (float)P.noise_energy_loss;
-        const double random_begin = (P.ambient_noise == 2)
-            ? (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 0u) * 1000.0 : 0.0;
-        const float out_scale = (float)(P.signal_max / (double)max_val);
-        const double ycoord1 = (double)col * 0.05, ycoord2 = (double)col * 0.2;
-        uint8_t* out = P.column_major
-            ? P.out + ((size_t)pose_i * P.az_count + (size_t)(az - P.az_begin)) * (size_t)C
-            : P.out + (size_t)pose_i * (size_t)C * RR_N_ANGLES + col;
-        for (int i = tid; i < C; i += RR_BLOCK) {
-            float v = s_col[i] * P.energy_max_f;
-            if (P.ambient_noise) {
-                double p = 0.0;
-                if (P.ambient_noise == 1) {
-                    p = (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 1u + (uint32_t)i);
-                } else if (P.ambient_noise == 2) {
-                    const double p1 = rr_perlin2(s_perm, random_begin + (double)i * 0.05, ycoord1);
-                    const double p2 = rr_perlin2(s_perm, random_begin + (double)i * 0.2, ycoord2);
-                    p = 0.9 * p1 + 0.1 * p2;
-                }
-                const float sn = (float)(1.0 - (double)((v - 0.0f) / signal_amp));
-                const float sn4 = (float)rr_pow4(sn);
-                const float amp = (float)((double)(sn4 * noise_at_0) + (1.0 - (double)sn4) * (double)noise_at_1);
-                float y = (float)((double)amp * p);
-                const float x = (float)(((double)(float)i + 0.5) * P.resolution);
-                y = y + (ne_max - ne_min) * rr_expf(-e_loss * x) + ne_min;
-                y = fabsf(y);
-                v = v + y;
+    /* ================= energy_max, ambient noise, normalise, mono8 (RadarCPU.cpp:453-542) ================= */
+    const int col = (P.scroll_image + az) % RR_N_ANGLES;
+    const uint64_t frame_id = P.frame_id0 + (uint64_t)pose_i;
+    const float signal_amp = max_val - 0.0f;
+    const float noise_at_0 = (float)((double)signal_amp * P.noise_at_signal_0);
+    const float noise_at_1 = (float)((double)signal_amp * P.noise_at_signal_1);
+    const float ne_max = (float)((double)max_val * P.noise_energy_max);
+    const float ne_min = (float)((double)max_val * P.noise_energy_min);
+    const float e_loss = (float)P.noise_energy_loss;
+    const double random_begin = (P.ambient_noise == 2)
+        ? (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 0u) * 1000.0 : 0.0;
+    const float out_scale = (float)(P.signal_max / (double)max_val);
+    const double ycoord1 = (double)col * 0.05, ycoord2 = (double)col * 0.2;
+    uint8_t* out = P.column_major
+        ? P.out + ((size_t)pose_i * P.az_count + (size_t)(az - P.az_begin)) * (size_t)C
+        : P.out + (size_t)pose_i * (size_t)C * RR_N_ANGLES + col;
+    for (int i = tid; i < C; i += RR_BLOCK) {
+        float v = s_col[i] * P.energy_max_f;
+        if (P.ambient_noise) {
+            double p = 0.0;
+            if (P.ambient_noise == 1) {
+                p = (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 1u + (uint32_t)i);
+            } else if (P.ambient_noise == 2) {
+                const double p1 = rr_perlin2(s_perm, random_begin + (double)i * 0.05, ycoord1);
+                const double p2 = rr_perlin2(s_perm, random_begin + (double)i * 0.2, ycoord2);
+                p = 0.9 * p1 + 0.1 * p2;
             }
-            v = v * out_scale;
-            if (DEBUG && P.dbg_columns) P.dbg_columns[(size_t)az * C + i] = v;
-            const uint8_t px = rr_to_u8(v);
-            if (P.column_major) out[i] = px; else out[(size_t)i * RR_N_ANGLES] = px;
+            const float sn = (float)(1.0 - (double)((v - 0.0f) / signal_amp));
+            const float sn4 = (float)rr_pow4(sn);
+            const float amp = (float)((double)(sn4 * noise_at_0) + (1.0 - (double)sn4) * (double)noise_at_1);
+            float y = (float)((double)amp * p);
+            const float x = (float)(((double)(float)i + 0.5) * P.resolution);
+            y = y + (ne_max - ne_min) * rr_expf(-e_loss * x) + ne_min;
+            y = fabsf(y);
+            v = v + y;
         }
+        v = v * out_scale;
+        if (DEBUG && P.dbg_columns) P.dbg_columns[(size_t)az * C + i] = v;
+        const uint8_t px = rr_to_u8(v);
+        if (P.column_major) out[i] = px; else out[(size_t)i * RR_N_ANGLES] = px;
+    }
 
-        /* ================= counters ================= */
-        if (STATS) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                stat_nodes += __shfl_xor_sync(RR_FULL, stat_nodes, off);
-                stat_tris += __shfl_xor_sync(RR_FULL, stat_tris, off);
-            }
-            if (lane == 0) {
-                atomicAdd(&P.counters[3], (unsigned long long)stat_nodes);
-                atomicAdd(&P.counters[4], (unsigned long long)stat_tris);
-            }
-        }
-        if (tid == 0) {
-            unsigned long long casts = 0, sigs = 0, mw = 0;
-            for (int p2 = 0; p2 < n_passes; p2++) {
-                casts += s_pass_waves[p2];
-                if (s_pass_waves[p2] > mw) mw = s_pass_waves[p2];
-                for (int w2 = 0; w2 < RR_WARPS; w2++) sigs += s_seg_count[p2][w2];
-            }
-            atomicAdd(&P.counters[0], casts);
-            atomicAdd(&P.counters[1], (unsigned long long)s_hits);
-            atomicAdd(&P.counters[2], sigs);
-            atomicMax(&P.counters[5], mw);
-        }
+    if (tid == 0) {
+        unsigned long long mw = 0;
+        for (int p2 = 0; p2 < n_passes; p2++) mw = max(mw, (unsigned long long)P.item_pass_waves[(size_t)item * RR_MAX_PASSES + p2]);
+        atomicMax(&P.counters[5], mw);
     }
 }
 
@@ -612,17 +618,24 @@ __global__ void rr_cast_kernel(const RRNode* nodes, const float4* tris, uint32_t
 }
 
 /* ---- host-side launchers (called from rr_api.cu) ------------------------------------------------*/
-extern "C" cudaError_t rr_launch_frame(const RRFrameParams* P, int grid, size_t smem, cudaStream_t st, int stats, int debug)
+extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int grid, cudaStream_t st, int stats, int debug)
 {
-    if (debug) rr_frame_kernel<true, true><<<grid, RR_BLOCK, smem, st>>>(*P);
-    else if (stats) rr_frame_kernel<true, false><<<grid, RR_BLOCK, smem, st>>>(*P);
-    else rr_frame_kernel<false, false><<<grid, RR_BLOCK, smem, st>>>(*P);
+    if (debug) rr_trace_kernel<true, true><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P);
+    else if (stats) rr_trace_kernel<true, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P);
+    else rr_trace_kernel<false, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P);
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t rr_frame_occupancy(int* blocks_per_sm, size_t smem)
+extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rr_frame_kernel<false, false>, RR_BLOCK, smem);
+    if (debug) rr_draw_kernel<true><<<n_items, RR_BLOCK, smem, st>>>(*P);
+    else rr_draw_kernel<false><<<n_items, RR_BLOCK, smem, st>>>(*P);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rr_trace_kernel<false, false>, RR_TRACE_BLOCK, 0);
 }
 
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
