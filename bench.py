@@ -109,28 +109,37 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_CPU_SCENE = {}
+
+
+def cpu_scene(scene):
+    """Reference-semantics CPU path, built once: oracle/_ref (the reference's OWN sources compiled against shims) when it
+    is present, else the oracle port. Returns (object with .simulate, kind)."""
+    if "obj" not in _CPU_SCENE:
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "libradarays_ref.so")
+        obj, kind = None, "port"
+        if os.path.exists(ref_so):
+            try:
+                from oracle import ref as oref
+                obj, kind = oref.RefScene(scene), "reference"
+            except Exception as e:  # fall back to the port, say so
+                print("bench: oracle/_ref unusable (%s), using the oracle port" % e, file=sys.stderr)
+        if obj is None:
+            from oracle import oracle
+            obj = oracle.OracleScene(scene)
+        _CPU_SCENE["obj"], _CPU_SCENE["kind"] = obj, kind
+    return _CPU_SCENE["obj"], _CPU_SCENE["kind"]
+
+
 def cpu_reference_run(scene, cfg, dirs, poses, n_frames, noise_seed):
-    """Reference-semantics CPU path on the host cores: oracle/_ref (the reference's own sources compiled against
-    shims) when it was built, else the oracle port. OpenMP over azimuths like RadarCPU.cpp:155."""
+    """n_frames frames on all host cores, OpenMP over azimuths like RadarCPU.cpp:155; timed by the CPU path's own
+    stopwatch around the azimuth loop (RadarCPU.cpp:147-148,550) — BVH build excluded."""
     cores = os.cpu_count() or 1
-    ref_so = os.path.join(ROOT, "oracle", "_ref", "libradarays_ref.so")
-    if os.path.exists(ref_so):
-        try:
-            from oracle import ref as oref
-            rs = oref.RefScene(scene)
-            t = 0.0
-            for i in range(n_frames):
-                t += rs.simulate(cfg, dirs, poses[i:i + 1], noise_seed=noise_seed, frame_id=i, threads=cores)["elapsed_s"]
-            return n_frames / t, "reference", cores, t
-        except Exception as e:  # fall back to the port, say so
-            print("bench: oracle/_ref unusable (%s), using the oracle port" % e, file=sys.stderr)
-    from oracle import oracle
-    osc = oracle.OracleScene(scene)
+    obj, kind = cpu_scene(scene)
     t = 0.0
     for i in range(n_frames):
-        t += osc.simulate(cfg, dirs, poses[i:i + 1], noise_seed=noise_seed, frame_id=i, threads=cores,
-                          want_columns=False)["elapsed_s"]
-    return n_frames / t, "port", cores, t
+        t += obj.simulate(cfg, dirs, poses[i:i + 1], noise_seed=noise_seed, frame_id=i, threads=cores)["elapsed_s"]
+    return n_frames / t, kind, cores, t
 
 
 def main():
@@ -220,6 +229,7 @@ def main():
         for w in range(W):
             step(w * POSES_PER_STEP)
     torch.cuda.synchronize()
+    radar.kernel_times()                                   # reset the per-kernel event ring
     sampler = ClockSampler(local_rank)
     sampler.start()
     if world > 1:
@@ -237,6 +247,7 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
+    trace_ms_sum, draw_ms_sum, n_pairs = radar.kernel_times()     # events around each kernel, on the launch stream
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
     img_sum = int(d_out.sum().item())
@@ -266,8 +277,10 @@ def main():
 
     if rank == 0:
         peak, peak_src = peak_hbm()
-        avg_launch_s = (total_ms / K) / 1000.0
-        achieved = alg_bytes / avg_launch_s / 1e9
+        # dominant kernel = rr_trace_kernel: its algorithmic gather bytes over ITS average launch duration
+        trace_bytes = 32 * nodes + 48 * tris + 4 * hits
+        avg_launch_s = (trace_ms_sum / max(n_pairs, 1)) / 1000.0
+        achieved = trace_bytes / avg_launch_s / 1e9
         traffic = None
         tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tr_path) and not args.small:
@@ -295,8 +308,12 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "formula": "32 B x nodes_visited + 48 B x tris_tested + 4 B x hits + n_angles x n_cells, per 16-pose launch (counted by the stats build)",
+                         "kernel": "rr_trace_kernel", "kernel_ms": trace_ms_sum / max(n_pairs, 1),
+                         "kernel_share_of_step": trace_ms_sum / max(trace_ms_sum + draw_ms_sum, 1e-9),
+                         "algorithmic_bytes_per_launch": trace_bytes,
+                         "formula": "32 B x nodes_visited + 48 B x tris_tested + 4 B x hits per 16-pose launch (counted by the stats build of the same kernel)",
+                         "draw_kernel_ms": draw_ms_sum / max(n_pairs, 1), "step_algorithmic_bytes": alg_bytes,
+                         "step_achieved_gbs": alg_bytes / ((total_ms / K) / 1000.0) / 1e9,
                          "nodes_visited": nodes, "tris_tested": tris},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cpu_cores, "kind": cpu_kind,
                              "sample": "%d frame(s) of the same workload (pose 0..), OpenMP over azimuths, %.1f s" % (args.cpu_frames, cpu_t)},

@@ -185,6 +185,11 @@ int         rr_cast_rays(rr_ctx* ctx, const float* origins_xyz, const float* dir
                          float tmax, int32_t* face_ids, float* ranges);
 
 int         rr_get_stats(rr_ctx* ctx, rr_stats* stats);       /* counters of the last call */
+
+/* Device time of the two kernels of the path, summed over the launch pairs enqueued since the previous call of this
+ * function (CUDA events recorded on the launch stream around rr_trace_kernel and rr_draw_kernel; up to 256 pairs are
+ * remembered). Synchronises the device. The reference's counterpart is its stdout stopwatch (RadarCPU.cpp:550-553). */
+int         rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_t* n_launch_pairs);
 int         rr_set_max_waves_per_azimuth(rr_ctx* ctx, uint32_t max_waves);
 
 #ifdef __cplusplus

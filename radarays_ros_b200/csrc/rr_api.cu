@@ -62,6 +62,10 @@ struct rr_ctx {
     rr_pose* h_poses = nullptr; size_t h_poses_cap = 0;
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;
     rr_stats last{};
+    /* per-kernel timing ring */
+    static const int kRing = 256;
+    cudaEvent_t tev[kRing][3] = {};
+    int tev_count = 0;
 };
 
 static int fail(rr_ctx* c, int code, const char* fmt, ...)
@@ -264,6 +268,7 @@ int rr_create(rr_ctx** out, int device_id)
     ctx->num_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    for (int i = 0; i < rr_ctx::kRing; i++) for (int k = 0; k < 3; k++) cudaEventCreate(&ctx->tev[i][k]);
     if ((e = cudaMalloc((void**)&ctx->d_work, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void**)&ctx->d_errflags, 4 * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -295,6 +300,7 @@ void rr_destroy(rr_ctx* ctx)
     cudaFree(ctx->d_poses); cudaFree(ctx->d_out);
     if (ctx->h_poses) cudaFreeHost(ctx->h_poses);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    for (int i = 0; i < rr_ctx::kRing; i++) for (int k = 0; k < 3; k++) if (ctx->tev[i][k]) cudaEventDestroy(ctx->tev[i][k]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -567,8 +573,13 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         CK(cudaMemsetAsync(ctx->d_ipw, 0, (size_t)items * RR_MAX_PASSES * sizeof(uint32_t), st));
         const uint32_t warps_per_cta = RR_TRACE_BLOCK / 32;
         const int grid = (int)std::min<uint32_t>((uint32_t)ctx->grid, (tasks + warps_per_cta - 1) / warps_per_cta);
+        const bool timed = ctx->tev_count < rr_ctx::kRing;
+        cudaEvent_t* te = ctx->tev[timed ? ctx->tev_count : 0];
+        if (timed) CK(cudaEventRecord(te[0], st));
         CK(rr_launch_trace(&P, std::max(grid, 1), st, stats, debug));
+        if (timed) CK(cudaEventRecord(te[1], st));
         CK(rr_launch_draw(&P, (int)items, (size_t)P.n_cells * sizeof(float), st, debug));
+        if (timed) { CK(cudaEventRecord(te[2], st)); ctx->tev_count++; }
     }
     P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0;
     return RR_OK;
@@ -654,6 +665,25 @@ int rr_simulate_device(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64
     P.az_begin = azimuth_begin; P.az_count = azimuth_count; P.frame_id0 = frame_id0;
     P.out = d_out_polar; P.column_major = column_major ? 1 : 0;
     return enqueue(ctx, P, (cudaStream_t)cuda_stream, 0, 0);
+}
+
+int rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_t* n_launch_pairs)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    float ts = 0.f, ds = 0.f;
+    for (int i = 0; i < ctx->tev_count; i++) {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, ctx->tev[i][0], ctx->tev[i][1]));
+        CK(cudaEventElapsedTime(&b, ctx->tev[i][1], ctx->tev[i][2]));
+        ts += a; ds += b;
+    }
+    if (trace_ms_sum) *trace_ms_sum = ts;
+    if (draw_ms_sum) *draw_ms_sum = ds;
+    if (n_launch_pairs) *n_launch_pairs = ctx->tev_count;
+    ctx->tev_count = 0;
+    return RR_OK;
 }
 
 int rr_get_stats(rr_ctx* ctx, rr_stats* stats)

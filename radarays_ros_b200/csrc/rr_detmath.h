@@ -24,8 +24,11 @@
 
 #if defined(__CUDACC__)
 #define RR_HD __host__ __device__ __forceinline__
+/* heavy transcendental bodies: real calls on the device keep the trace kernel's code inside the instruction cache */
+#define RR_HD_CALL static __host__ __device__ __noinline__
 #else
 #define RR_HD static inline
+#define RR_HD_CALL static inline
 #endif
 
 /* ------------------------------------------------------------------------------------------------
@@ -95,7 +98,7 @@ RR_HD double rr_rem_pio2(double x, int* quadrant)
  * pure selections/quotients of (s, c), so evaluating the pair once and deriving several functions from it gives
  * exactly the bits of the separate calls (the frame kernel does that for sin and tan of the same angle). */
 typedef struct { double s, c; int q; } rr_sincos_t;
-RR_HD rr_sincos_t rr_sincos_parts(double x)
+RR_HD_CALL rr_sincos_t rr_sincos_parts(double x)
 {
     rr_sincos_t r;
     if (!(fabs(x) < 1.0e5)) { r.s = x - x; r.c = x - x; r.q = 0; return r; }   /* NaN for inf/NaN/out-of-domain */
@@ -149,7 +152,7 @@ RR_HD double rr_kasin(double x)  /* |x| <= 0.5 */
     return fma(x * z, p, x);
 }
 
-RR_HD double rr_asin(double x)
+RR_HD_CALL double rr_asin(double x)
 {
     const double ax = fabs(x);
     if (!(ax <= 1.0)) return (x - x) / (x - x); /* NaN outside [-1,1] (and for NaN) */
@@ -160,7 +163,7 @@ RR_HD double rr_asin(double x)
     return (x < 0.0) ? -r : r;
 }
 
-RR_HD double rr_acos(double x)
+RR_HD_CALL double rr_acos(double x)
 {
     const double ax = fabs(x);
     if (!(ax <= 1.0)) return (x - x) / (x - x);
@@ -179,7 +182,7 @@ RR_HD float rr_cosf(float x)  { return (float)rr_cos((double)x); }
 /* ------------------------------------------------------------------------------------------------
  * exp / log (double) — enough range for results that are consumed as float
  * ---------------------------------------------------------------------------------------------- */
-RR_HD double rr_exp(double x)
+RR_HD_CALL double rr_exp(double x)
 {
     if (x != x) return x;
     if (x > 709.0) return rr_u2d(0x7ff0000000000000ull);
@@ -207,7 +210,7 @@ RR_HD double rr_exp(double x)
     return p * rr_u2d((uint64_t)(k + 1023) << 52);
 }
 
-RR_HD double rr_log(double x)   /* x > 0, finite, normal */
+RR_HD_CALL double rr_log(double x)   /* x > 0, finite, normal */
 {
     uint64_t u = rr_d2u(x);
     int e = (int)(u >> 52) - 1023;
@@ -239,7 +242,7 @@ RR_HD float rr_expf(float x) { return (float)rr_exp((double)x); }
 
 /* powf(x, y) with C99 special cases for the inputs the BRDF produces (radar_algorithms.h:181:
  * pow(cos(angle), specular_exp), both float). */
-RR_HD float rr_powf(float x, float y)
+RR_HD_CALL float rr_powf(float x, float y)
 {
     if (y == 0.0f || x == 1.0f) return 1.0f;
     if (x != x || y != y) return x + y;

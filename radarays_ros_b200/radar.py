@@ -157,6 +157,12 @@ class RadarB200:
         capi.check(self._ctx, self._lib.rr_get_stats(self._ctx, C.byref(st)))
         return st
 
+    def kernel_times(self):
+        """(trace_ms_sum, draw_ms_sum, n_launch_pairs) since the previous call; synchronises."""
+        t, d, n = C.c_float(0), C.c_float(0), C.c_int32(0)
+        capi.check(self._ctx, self._lib.rr_kernel_times(self._ctx, C.byref(t), C.byref(d), C.byref(n)))
+        return t.value, d.value, n.value
+
     # ---- parity probes -------------------------------------------------------------------------------------------
     def debug_trace(self, Tsm, frame_id=0, capacity=None):
         arr = self._poses(Tsm)
