@@ -44,6 +44,7 @@ struct RRBuildNode {
 #define RR_WARPS (RR_BLOCK / 32)
 #define RR_TRACE_BLOCK 128       /* trace kernel: 4 independent warps per CTA */
 #define RR_CHUNK 32              /* beam samples per trace task (= one warp) */
+#define RR_MAX_GRANULES 320      /* ceil(10000 cells / 32) rounded up */
 #define RR_MAX_PASSES 20         /* cfg/RadarModel.cfg:27 n_reflections <= 20 */
 
 struct RRFrameParams {

@@ -70,8 +70,12 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
     int best_face = -1, best_slot = -1;
     float limit = tmax * 1.00001f + 1e-6f;        /* prune slack >> rounding error of t (ties must be visited) */
 
-    while (true) {
-        if (!(cur & RR_REF_LEAF)) {
+    /* while-while walk: every lane first descends through inner nodes until it holds a leaf (or has nothing left); the
+     * lanes of the warp reconverge after the inner loop, so the triangle tests below run once per round with (nearly)
+     * all lanes on a leaf instead of being replayed for one or two lanes between node steps. RR_REF_EMPTY (which has
+     * the leaf bit set, so it also ends the inner loop) marks a finished lane. */
+    while (cur != RR_REF_EMPTY) {
+        while (!(cur & RR_REF_LEAF)) {
             const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
             const uint4 a = __ldg(np);           /* c0.x c0.y c0.z c1.x */
             const uint4 b = __ldg(np + 1);       /* c1.y c1.z ref0 ref1 */
@@ -95,10 +99,10 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
             } else if (h1) {
                 cur = b.w;
             } else {
-                if (sp == 0) break;
-                cur = stack[--sp];
+                cur = (sp > 0) ? stack[--sp] : RR_REF_EMPTY;
             }
-        } else {
+        }
+        if (cur != RR_REF_EMPTY) {
             const uint32_t first = cur & 0x0fffffffu;
             const uint32_t cnt = ((cur >> 28) & 7u) + 1u;
             for (uint32_t k = 0; k < cnt; k++) {
@@ -115,8 +119,7 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
                     }
                 }
             }
-            if (sp == 0) break;
-            cur = stack[--sp];
+            cur = (sp > 0) ? stack[--sp] : RR_REF_EMPTY;
         }
     }
     t_hit = best_t;
@@ -469,19 +472,22 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
  * Kernel 2/2: rr_draw_kernel — returns -> range column (RadarCPU.cpp:402-450) -> energy_max, ambient noise,
  * normalise, mono8 (RadarCPU.cpp:453-542). One CTA per (pose, azimuth); the column lives in shared memory.
  *
- * Accumulation is in the reference's order WITHOUT atomics: bins are dealt to the warps in 32-bin granules,
- * round-robin (granule G belongs to warp G % 8, bin g to lane g % 32), so a bin always has the same owner thread and
- * sees its additions in program order = list order; a W <= 200 wide splat touches at most one granule per warp.
- * Every warp replays the (pass, chunk) segments; 32 returns are tested at once (ballot) and only the ones touching
- * this warp's granules are applied. The float column is therefore bit-identical to the sequential reference loop.
+ * Accumulation is in the reference's order WITHOUT atomics: every bin has exactly one owner thread (its warp by a
+ * per-item partition of the column into contiguous 32-bin-granule ranges, its lane by g & 31), so a bin sees its
+ * additions in program order = list order and the float column is bit-identical to the sequential reference loop.
+ * Returns cluster in range (a wall = a few hundred adjacent bins), so the partition is ADAPTIVE: a shared-memory
+ * histogram of splat load per granule is prefix-summed and cut into 8 ranges of equal load. Every warp replays the
+ * (pass, chunk) segments; 32 returns are tested at once (ballot) and only those overlapping its range are applied.
  * ---------------------------------------------------------------------------------------------- */
 template <bool DEBUG>
 __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P)
 {
     extern __shared__ float s_col[];                     /* n_cells floats: this azimuth's range column */
-    __shared__ float s_weights[RR_MAX_DENOISE];
+    __shared__ double s_weights[RR_MAX_DENOISE];         /* float weights widened once (the splat multiplies in double) */
     __shared__ unsigned char s_perm[256];
     __shared__ float s_red[RR_WARPS];
+    __shared__ uint32_t s_load[RR_MAX_GRANULES];
+    __shared__ int s_bound[RR_WARPS + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t item = blockIdx.x;
@@ -490,16 +496,67 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     const int C = P.n_cells;
     const int n_passes = P.n_passes;
     const uint32_t n_chunks = (uint32_t)P.n_chunks, scap = P.sig_cap_w;
-    for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? P.denoise_weights[i] : 0.f;
+    for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? (double)P.denoise_weights[i] : 0.0;
     for (int i = tid; i < 256; i += RR_BLOCK) s_perm[i] = c_perlin_perm[i];
+    const int n_gran = (C + 31) >> 5;                              /* <= 313 for n_cells <= 10000 */
     for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
+    for (int i = tid; i < RR_MAX_GRANULES; i += RR_BLOCK) s_load[i] = 0u;
     __syncthreads();
 
+    const int W = P.denoise_on ? P.denoise_width : 1;
+    const int mode = P.denoise_on ? P.denoise_mode : 0;
+    const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
+
+    /* ---- 1. splat load per 32-bin granule (any order: integer atomics) */
+    for (uint32_t ch = 0; ch < n_chunks; ch++) {
+        const size_t task = (size_t)item * n_chunks + ch;
+        const uint32_t* seg = P.seg_counts + task * RR_MAX_PASSES;
+        uint32_t n_ret = 0;
+        for (int p2 = 0; p2 < n_passes; p2++) n_ret += seg[p2];
+        const int32_t* pc = P.sig_cell + task * scap;
+        for (uint32_t k = tid; k < n_ret; k += RR_BLOCK) {
+            const int cell = pc[k];
+            if (!(cell < C) || !(cell > -RR_MAX_DENOISE - 1)) continue;
+            const int st = cell - mode;
+            const int g_lo = max(st, lo_bin) >> 5, g_hi = (min(st + W, C) - 1) >> 5;
+            for (int g = g_lo; g <= g_hi; g++) atomicAdd(&s_load[g], 1u);
+        }
+    }
+    __syncthreads();
+    /* ---- 2. cut the granules into RR_WARPS contiguous ranges of (nearly) equal load */
+    if (wid == 0) {
+        uint32_t run = 0;                                             /* inclusive prefix over granules, 32 at a time */
+        uint32_t total = 0;
+        for (int base = 0; base < n_gran; base += 32) total += __reduce_add_sync(RR_FULL, (base + lane < n_gran) ? s_load[base + lane] : 0u);
+        if (lane <= RR_WARPS) s_bound[lane] = (lane == RR_WARPS) ? n_gran : 0;
+        __syncwarp();
+        for (int base = 0; base < n_gran; base += 32) {
+            const uint32_t v = (base + lane < n_gran) ? s_load[base + lane] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const uint32_t nb = __shfl_up_sync(RR_FULL, incl, off); if (lane >= off) incl += nb; }
+            const uint32_t before = run + incl - v, after = run + incl;
+            /* granule (base+lane) opens range w when the load before it is <= w*total/8 < load after it */
+            if (base + lane < n_gran && v > 0) {
+                for (int w = 1; w < RR_WARPS; w++) {
+                    const uint32_t cut = (uint32_t)(((unsigned long long)total * (unsigned)w) / RR_WARPS);
+                    if (before <= cut && cut < after) s_bound[w] = base + lane + ((cut - before) * 2 >= v ? 1 : 0);
+                }
+            }
+            run += __shfl_sync(RR_FULL, incl, 31);
+        }
+        __syncwarp();
+        if (lane == 0) {                                              /* monotone, inside [0, n_gran] */
+            int prev = 0;
+            for (int w = 1; w < RR_WARPS; w++) { int bnd = (total == 0) ? (w * n_gran) / RR_WARPS : s_bound[w]; bnd = max(prev, min(bnd, n_gran)); s_bound[w] = bnd; prev = bnd; }
+        }
+    }
+    __syncthreads();
+    const int my_lo = s_bound[wid] << 5, my_hi = min(C, s_bound[wid + 1] << 5);   /* this warp's bins [my_lo, my_hi) */
+
+    /* ---- 3. ordered accumulation */
     float m = 0.0f;
-    {
-        const int W = P.denoise_on ? P.denoise_width : 1;
-        const int mode = P.denoise_on ? P.denoise_mode : 0;
-        const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
+    if (my_lo < my_hi) {
         for (int pass = 0; pass < n_passes; pass++) {
             for (uint32_t ch = 0; ch < n_chunks; ch++) {
                 const size_t task = (size_t)item * n_chunks + ch;
@@ -515,22 +572,21 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
                     const int cell = valid ? pc[base + lane] : 0;
                     const float str = valid ? pst[base + lane] : 0.f;
                     /* cell < C (:414); very negative cells (time = -inf/NaN) can not reach a bin */
-                    bool rel = valid && (cell < C) && (cell > -RR_MAX_DENOISE - 1);
                     const int start = cell - mode;
-                    const int gs0 = start >> 5, ge0 = (start + W - 1) >> 5;
-                    rel = rel && (gs0 + ((wid - gs0) & (RR_WARPS - 1)) <= ge0);
+                    const bool rel = valid && (cell < C) && (cell > -RR_MAX_DENOISE - 1)
+                                     && (max(start, lo_bin) < my_hi) && (min(start + W, C) > my_lo);
                     uint32_t mask = __ballot_sync(RR_FULL, rel);
                     while (mask) {
                         const int j = __ffs(mask) - 1;
                         mask &= mask - 1;
                         const int st = __shfl_sync(RR_FULL, start, j);
                         const float sv = __shfl_sync(RR_FULL, str, j);
-                        const int g0 = st >> 5;
-                        const int g = ((g0 + ((wid - g0) & (RR_WARPS - 1))) << 5) + lane;
-                        if (g >= max(st, lo_bin) && g < min(st + W, C)) {
+                        const double svd = (double)sv;
+                        const int lo = max(max(st, lo_bin), my_lo), hi = min(min(st + W, C), my_hi);
+                        for (int g = lo + ((lane - lo) & 31); g < hi; g += 32) {     /* bin g <-> lane g & 31, always */
                             float v;
                             if (P.denoise_on) {
-                                v = (float)((double)s_col[g] + (double)sv * (double)s_weights[g - st]);
+                                v = (float)((double)s_col[g] + svd * s_weights[g - st]);
                             } else {
                                 const float old = s_col[g];
                                 v = (old < sv) ? sv : old;                 /* std::max(old, strength), :439 */
