@@ -191,6 +191,11 @@ int         rr_get_stats(rr_ctx* ctx, rr_stats* stats);       /* counters of the
  * remembered). Synchronises the device. The reference's counterpart is its stdout stopwatch (RadarCPU.cpp:550-553). */
 int         rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_t* n_launch_pairs);
 int         rr_set_max_waves_per_azimuth(rr_ctx* ctx, uint32_t max_waves);
+/* Concurrency inside one call: the poses of a call are cut into sub-batches that alternate between `n_lanes` internal
+ * streams (default 2, each with its own wave lists), so one sub-batch's pass tails, draw kernel and device->host copy
+ * overlap the other's traversal. 1 = strictly serial launches, which is what rr_kernel_times needs to time a kernel
+ * alone. Results do not depend on it. (The reference's counterpart is its OpenMP fan-out, RadarCPU.cpp:155.) */
+int         rr_set_lanes(rr_ctx* ctx, int32_t n_lanes);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ SYMBOLS = [
     "rr_abi_version", "rr_config_defaults", "rr_model_defaults", "rr_create", "rr_destroy", "rr_last_error",
     "rr_set_mesh", "rr_set_materials", "rr_set_params", "rr_set_beam_samples", "rr_get_beam_samples",
     "rr_set_noise_seed", "rr_simulate", "rr_simulate_motion", "rr_simulate_device", "rr_simulate_stats",
-    "rr_debug_trace", "rr_cast_rays", "rr_get_stats", "rr_set_max_waves_per_azimuth", "rr_kernel_times",
+    "rr_debug_trace", "rr_cast_rays", "rr_get_stats", "rr_set_max_waves_per_azimuth", "rr_kernel_times", "rr_set_lanes",
 ]
 
 
@@ -52,6 +52,7 @@ def lib():
     L.rr_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.rr_set_max_waves_per_azimuth.argtypes = [vp, C.c_uint32]
     L.rr_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i32)]
+    L.rr_set_lanes.argtypes = [vp, i32]
     for name in SYMBOLS:
         getattr(L, name).restype = C.c_int
     L.rr_last_error.restype = C.c_char_p

@@ -13,7 +13,8 @@
 #include "rr_bvh.h"
 #include "rr_internal.h"
 
-extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int grid, cudaStream_t st, int stats, int debug);
+extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats, int debug);
+extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStream_t st);
 extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
@@ -50,12 +51,27 @@ struct rr_ctx {
     float4* d_tas = nullptr;
     uint64_t noise_seed = 0;
     uint32_t max_waves_user = 0;
-    /* scratch */
-    int grid = 0; uint32_t wave_cap = 0, sig_cap = 0;
-    float* d_wave_f32 = nullptr; double* d_wave_f64 = nullptr; uint32_t* d_wave_mat = nullptr;
-    int32_t* d_sig_cell = nullptr; float* d_sig_str = nullptr; uint32_t* d_seg = nullptr; uint32_t* d_ipw = nullptr;
-    uint32_t n_chunks = 0, max_items = 0;          /* items (pose, azimuth) one launch pair can hold */
-    uint32_t* d_work = nullptr; unsigned long long* d_counters = nullptr; int32_t* d_errflags = nullptr;
+    /* scratch (wavefront lists, rr_internal.h): one set per LANE. A lane is a stream with its own lists; a call's poses
+     * are cut into sub-batches that alternate between the lanes, so the tail of one sub-batch's pass (few long rays left)
+     * and its draw kernel overlap the other lane's traversal, and device->host copies overlap compute. */
+    static const int kLanes = 2;
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        float* d_wave_f32 = nullptr; double* d_wave_f64 = nullptr; uint32_t* d_wave_mat = nullptr; uint32_t* d_wave_item = nullptr;
+        uint32_t* d_group_base = nullptr; uint32_t* d_first_src = nullptr; uint32_t* d_item_start = nullptr;
+        uint32_t* d_super = nullptr; uint32_t* d_item_super = nullptr;
+        int2* d_sig_cell = nullptr; float2* d_sig_str = nullptr;
+        uint32_t* d_ctrl = nullptr;                /* pass_total[RR_MAX_PASSES + 1] | work_counter[RR_MAX_PASSES] */
+    } lanes[kLanes];
+    int n_lanes = kLanes;                          /* rr_set_lanes: 1 = serial launches (per-kernel timing) */
+    cudaEvent_t fork_ev = nullptr;
+    std::vector<cudaEvent_t> sub_ev;               /* one per sub-batch of the host path (copy finished) */
+    int grid = 0;
+    uint32_t waves_per_item = 0, wave_cap = 0, max_items = 0;   /* list capacity: per item, per lane; items per launch sequence */
+    uint32_t super_stride = 0, item_super_stride = 0;
+    uint32_t alloc_passes = 0, alloc_samples = 0;
+    unsigned long long* d_counters = nullptr; int32_t* d_errflags = nullptr;
     /* host-buffer path staging */
     rr_pose* d_poses = nullptr; size_t d_poses_cap = 0;
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
@@ -66,6 +82,7 @@ struct rr_ctx {
     static const int kRing = 256;
     cudaEvent_t tev[kRing][3] = {};
     int tev_count = 0;
+    unsigned long long launches = 0;           /* kernels launched since rr_create (rr_kernel_launches) */
 };
 
 static int fail(rr_ctx* c, int code, const char* fmt, ...)
@@ -219,6 +236,20 @@ void draw_beam_samples(float width, int n, int dist, float p_in_cone, uint64_t s
 } // namespace
 
 /* ---------------------------------------------------------------------------------------------------------*/
+static void free_lane_scratch(rr_ctx* ctx)
+{
+    for (int l = 0; l < rr_ctx::kLanes; l++) {
+        rr_ctx::Lane& L = ctx->lanes[l];
+        cudaFree(L.d_wave_f32); cudaFree(L.d_wave_f64); cudaFree(L.d_wave_mat); cudaFree(L.d_wave_item);
+        cudaFree(L.d_sig_cell); cudaFree(L.d_sig_str); cudaFree(L.d_group_base); cudaFree(L.d_first_src);
+        cudaFree(L.d_item_start); cudaFree(L.d_super); cudaFree(L.d_item_super);
+        L.d_wave_f32 = nullptr; L.d_wave_f64 = nullptr; L.d_wave_mat = nullptr; L.d_wave_item = nullptr;
+        L.d_sig_cell = nullptr; L.d_sig_str = nullptr; L.d_group_base = nullptr; L.d_first_src = nullptr;
+        L.d_item_start = nullptr; L.d_super = nullptr; L.d_item_super = nullptr;
+    }
+    ctx->grid = 0; ctx->max_items = 0;
+}
+
 extern "C" {
 
 int rr_abi_version(void) { return RR_ABI_VERSION; }
@@ -269,7 +300,12 @@ int rr_create(rr_ctx** out, int device_id)
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     for (int i = 0; i < rr_ctx::kRing; i++) for (int k = 0; k < 3; k++) cudaEventCreate(&ctx->tev[i][k]);
-    if ((e = cudaMalloc((void**)&ctx->d_work, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    for (int l = 0; l < rr_ctx::kLanes; l++) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaMalloc((void**)&ctx->lanes[l].d_ctrl, (2 * RR_MAX_PASSES + 1) * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void**)&ctx->d_errflags, 4 * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void**)&ctx->d_tas, RR_N_ANGLES * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -294,9 +330,15 @@ void rr_destroy(rr_ctx* ctx)
     cudaDeviceSynchronize();
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials);
     cudaFree(ctx->d_weights); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
-    cudaFree(ctx->d_wave_f32); cudaFree(ctx->d_wave_f64); cudaFree(ctx->d_wave_mat);
-    cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str); cudaFree(ctx->d_seg); cudaFree(ctx->d_ipw);
-    cudaFree(ctx->d_work); cudaFree(ctx->d_counters); cudaFree(ctx->d_errflags);
+    free_lane_scratch(ctx);
+    for (int l = 0; l < rr_ctx::kLanes; l++) {
+        cudaFree(ctx->lanes[l].d_ctrl);
+        if (ctx->lanes[l].done) cudaEventDestroy(ctx->lanes[l].done);
+        if (ctx->lanes[l].stream) cudaStreamDestroy(ctx->lanes[l].stream);
+    }
+    for (cudaEvent_t ev : ctx->sub_ev) cudaEventDestroy(ev);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_errflags);
     cudaFree(ctx->d_poses); cudaFree(ctx->d_out);
     if (ctx->h_poses) cudaFreeHost(ctx->h_poses);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -484,41 +526,47 @@ static int ready(rr_ctx* ctx)
     return ensure_beam(ctx);
 }
 
-/* Scratch: wave lists per resident trace warp; return buffers per task, for up to `want_items` items per launch pair
- * (bounded to ~1.5 GB; larger batches are processed in several launch pairs by the callers). */
+/* Scratch per lane: the two wave buffers, group/item prefix tables and per-wave return slots for up to `want_items`
+ * items per launch sequence (each lane bounded to ~4 GB of the 180 GB; larger batches run as several sequences). */
 static int ensure_scratch(rr_ctx* ctx, size_t want_items)
 {
     int per_sm = 0;
     CK(rr_trace_occupancy(&per_sm));
     if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "trace kernel does not fit on an SM");
     const int grid = ctx->num_sms * per_sm;
-    const uint32_t S = ctx->model.n_samples, Pn = ctx->model.n_reflections;
-    const uint32_t n_chunks = (S + RR_CHUNK - 1) / RR_CHUNK;
-    uint32_t cap_w;
-    if (ctx->max_waves_user) cap_w = (ctx->max_waves_user + n_chunks - 1) / n_chunks;
-    else cap_w = RR_CHUNK * (1u << std::min<uint32_t>(Pn > 0 ? Pn - 1 : 0, 3));   /* room for 3 dielectric splits per path */
-    cap_w = std::max<uint32_t>(cap_w, RR_CHUNK);
-    cap_w = (cap_w + 31u) & ~31u;
-    const uint32_t scap_w = 2u * cap_w * std::max<uint32_t>(1, std::min<uint32_t>(Pn, 6));
-    const size_t per_item = (size_t)n_chunks * ((size_t)scap_w * 8 + RR_MAX_PASSES * 4) + RR_MAX_PASSES * 4;
-    size_t max_items = std::max<size_t>(RR_N_ANGLES, (size_t)1536 * 1024 * 1024 / per_item);
+    const uint32_t S = ctx->model.n_samples, Pn = std::max<uint32_t>(1, ctx->model.n_reflections);
+    /* longest per-azimuth wave list a pass may reach: user value, else room for 3 dielectric splits per path */
+    uint32_t wpi = ctx->max_waves_user ? ctx->max_waves_user : S * (1u << std::min<uint32_t>(Pn - 1, 3));
+    wpi = std::max<uint32_t>(wpi, S);
+    const size_t per_wave = 2 /*buffers*/ * 2 /*slots*/ * 48 + (size_t)Pn * 16 + 2;
+    const size_t per_item = (size_t)wpi * per_wave + (size_t)(Pn + 1) * 4;
+    size_t max_items = std::max<size_t>(RR_N_ANGLES, ((size_t)4 << 30) / per_item);
     max_items = std::min<size_t>(max_items, std::max<size_t>(want_items, RR_N_ANGLES));
-    if (grid != ctx->grid || cap_w != ctx->wave_cap || scap_w != ctx->sig_cap || n_chunks != ctx->n_chunks || max_items > ctx->max_items) {
-        cudaFree(ctx->d_wave_f32); cudaFree(ctx->d_wave_f64); cudaFree(ctx->d_wave_mat); cudaFree(ctx->d_sig_cell); cudaFree(ctx->d_sig_str);
-        cudaFree(ctx->d_seg); cudaFree(ctx->d_ipw);
-        ctx->d_wave_f32 = nullptr; ctx->d_wave_f64 = nullptr; ctx->d_wave_mat = nullptr; ctx->d_sig_cell = nullptr; ctx->d_sig_str = nullptr;
-        ctx->d_seg = nullptr; ctx->d_ipw = nullptr;
-        ctx->grid = 0; ctx->max_items = 0;
-        const size_t warps = (size_t)grid * (RR_TRACE_BLOCK / 32);
-        const size_t tasks = max_items * n_chunks;
-        CK(cudaMalloc((void**)&ctx->d_wave_f32, warps * 2 * 6 * cap_w * sizeof(float)));
-        CK(cudaMalloc((void**)&ctx->d_wave_f64, warps * 2 * 2 * cap_w * sizeof(double)));
-        CK(cudaMalloc((void**)&ctx->d_wave_mat, warps * 2 * cap_w * sizeof(uint32_t)));
-        CK(cudaMalloc((void**)&ctx->d_sig_cell, tasks * scap_w * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&ctx->d_sig_str, tasks * scap_w * sizeof(float)));
-        CK(cudaMalloc((void**)&ctx->d_seg, tasks * RR_MAX_PASSES * sizeof(uint32_t)));
-        CK(cudaMalloc((void**)&ctx->d_ipw, max_items * RR_MAX_PASSES * sizeof(uint32_t)));
-        ctx->grid = grid; ctx->wave_cap = cap_w; ctx->sig_cap = scap_w; ctx->n_chunks = n_chunks; ctx->max_items = (uint32_t)max_items;
+    while (max_items > RR_N_ANGLES && max_items * wpi > 0x7fffff00ull) max_items -= RR_N_ANGLES;
+    if (max_items * wpi > 0x7fffff00ull) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "max_waves_per_azimuth %u is too large", wpi);
+    if (grid != ctx->grid || wpi != ctx->waves_per_item || Pn != ctx->alloc_passes || S != ctx->alloc_samples || max_items > ctx->max_items) {
+        CK(cudaDeviceSynchronize());
+        free_lane_scratch(ctx);
+        const size_t wave_cap = ((size_t)max_items * wpi + 31) & ~(size_t)31;
+        const size_t slot_cap = 2 * wave_cap, group_cap = wave_cap / 32;
+        const size_t super_stride = group_cap / RR_SCAN_BLOCK + 2, item_super_stride = max_items / RR_SCAN_BLOCK + 2;
+        for (int l = 0; l < rr_ctx::kLanes; l++) {
+            rr_ctx::Lane& L = ctx->lanes[l];
+            CK(cudaMalloc((void**)&L.d_wave_f32, 2 * 6 * slot_cap * sizeof(float)));
+            CK(cudaMalloc((void**)&L.d_wave_f64, 2 * 2 * slot_cap * sizeof(double)));
+            CK(cudaMalloc((void**)&L.d_wave_mat, 2 * slot_cap * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_wave_item, 2 * slot_cap * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_group_base, 2 * (group_cap + 1) * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_first_src, (group_cap + 1) * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_item_start, (size_t)(Pn + 1) * (max_items + 1) * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_super, (size_t)(Pn + 1) * super_stride * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_item_super, (size_t)(Pn + 1) * item_super_stride * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_sig_cell, (size_t)Pn * wave_cap * sizeof(int2)));
+            CK(cudaMalloc((void**)&L.d_sig_str, (size_t)Pn * wave_cap * sizeof(float2)));
+        }
+        ctx->grid = grid; ctx->waves_per_item = wpi; ctx->alloc_passes = Pn; ctx->alloc_samples = S;
+        ctx->wave_cap = (uint32_t)wave_cap; ctx->max_items = (uint32_t)max_items;
+        ctx->super_stride = (uint32_t)super_stride; ctx->item_super_stride = (uint32_t)item_super_stride;
     }
     return RR_OK;
 }
@@ -544,42 +592,95 @@ static void fill_params(rr_ctx* ctx, RRFrameParams& P)
     P.record_multi_reflection = c.record_multi_reflection; P.record_multi_path = c.record_multi_path;
     P.multipath_threshold = c.multipath_threshold;
     P.noise_seed = ctx->noise_seed;
-    P.wave_f32 = ctx->d_wave_f32; P.wave_f64 = ctx->d_wave_f64; P.wave_mat = ctx->d_wave_mat;
-    P.sig_cell = ctx->d_sig_cell; P.sig_strength = ctx->d_sig_str; P.wave_cap_w = ctx->wave_cap; P.sig_cap_w = ctx->sig_cap;
-    P.seg_counts = ctx->d_seg; P.item_pass_waves = ctx->d_ipw; P.n_chunks = (int32_t)ctx->n_chunks;
-    P.work_counter = ctx->d_work; P.counters = ctx->d_counters; P.error_flags = ctx->d_errflags;
+    P.counters = ctx->d_counters; P.error_flags = ctx->d_errflags;
 }
 
-/* One launch pair (trace + draw) per sub-batch of poses; counters accumulate over the whole call. */
-static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, int debug)
+static void bind_lane(rr_ctx* ctx, RRFrameParams& P, int lane)
+{
+    const rr_ctx::Lane& L = ctx->lanes[lane];
+    P.wave_f32 = L.d_wave_f32; P.wave_f64 = L.d_wave_f64; P.wave_mat = L.d_wave_mat; P.wave_item = L.d_wave_item;
+    P.group_base = L.d_group_base; P.first_src = L.d_first_src; P.item_start = L.d_item_start;
+    P.super_count = L.d_super; P.item_super = L.d_item_super;
+    P.sig_cell = L.d_sig_cell; P.sig_strength = L.d_sig_str;
+    P.pass_total = L.d_ctrl; P.work_counter = L.d_ctrl + (RR_MAX_PASSES + 1);
+}
+
+/* Host-path options of enqueue(): copy every finished sub-batch to `h_dst` on its lane and mark it with an event. */
+struct RRCopyOut { uint8_t* h_dst = nullptr; int n_sub = 0; std::vector<std::pair<int, int>> ranges; };
+
+/* The poses of a call are cut into sub-batches; each sub-batch is one launch sequence (trace pass 0, scan, trace pass 1,
+ * ..., draw) on a lane's stream. The lanes fork from `st` and join it again at the end, so to the caller everything is
+ * ordered on `st`. Nothing here waits for the device: list lengths stay in device memory (pass_total). Counters
+ * accumulate over the whole call. `min_split` asks for at least that many sub-batches (pipelining of the copies). */
+static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, int debug, int min_split = 0, RRCopyOut* copy = nullptr)
 {
     CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->d_errflags, 0, 4 * sizeof(int32_t), st));
     const int n_total = P.n_poses;
-    const int poses_per_launch = std::max<int>(1, (int)(ctx->max_items / (uint32_t)P.az_count));
+    const int n_lanes = (stats || debug) ? 1 : std::max(1, std::min(ctx->n_lanes, (int)rr_ctx::kLanes));
+    const int want_split = std::max(min_split, n_lanes);
+    int poses_per_launch = std::max<int>(1, (int)(ctx->max_items / (uint32_t)P.az_count));
+    poses_per_launch = std::max(1, std::min(poses_per_launch, (n_total + want_split - 1) / want_split));
     const rr_pose* poses0 = P.poses;
     uint8_t* out0 = P.out;
     const uint64_t frame0 = P.frame_id0;
     const size_t out_stride = P.column_major ? (size_t)P.az_count * P.n_cells : (size_t)P.n_cells * RR_N_ANGLES;
-    for (int first = 0; first < n_total; first += poses_per_launch) {
+    const int Pn = P.n_passes;
+    const int n_sub = (n_total + poses_per_launch - 1) / poses_per_launch;
+    const int lanes_used = std::min(n_lanes, n_sub);
+    if (copy) {
+        while ((int)ctx->sub_ev.size() < n_sub) {
+            cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); ctx->sub_ev.push_back(ev);
+        }
+        copy->n_sub = n_sub; copy->ranges.clear();
+    }
+    CK(cudaEventRecord(ctx->fork_ev, st));
+    for (int l = 0; l < lanes_used; l++) CK(cudaStreamWaitEvent(ctx->lanes[l].stream, ctx->fork_ev, 0));
+    int sub = 0;
+    for (int first = 0; first < n_total; first += poses_per_launch, sub++) {
+        const int lane = sub % lanes_used;
+        cudaStream_t ls = ctx->lanes[lane].stream;
+        bind_lane(ctx, P, lane);
         const int n = std::min(poses_per_launch, n_total - first);
         P.n_poses = n;
         P.poses = poses0 + (size_t)first * (P.pose_per_azimuth ? RR_N_ANGLES : 1);
         P.out = out0 + (size_t)first * out_stride;
         P.frame_id0 = frame0 + (uint64_t)first;
         const uint32_t items = (uint32_t)n * (uint32_t)P.az_count;
-        const uint32_t tasks = items * (uint32_t)P.n_chunks;
-        CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(uint32_t), st));
-        CK(cudaMemsetAsync(ctx->d_ipw, 0, (size_t)items * RR_MAX_PASSES * sizeof(uint32_t), st));
-        const uint32_t warps_per_cta = RR_TRACE_BLOCK / 32;
-        const int grid = (int)std::min<uint32_t>((uint32_t)ctx->grid, (tasks + warps_per_cta - 1) / warps_per_cta);
+        P.n_items = (int32_t)items;
+        P.wave_cap = (uint32_t)((((size_t)items * ctx->waves_per_item) + 31) & ~(size_t)31);
+        P.slot_cap = 2 * P.wave_cap; P.group_cap = P.wave_cap / 32; P.item_stride = items + 1;
+        P.super_stride = ctx->super_stride; P.item_super_stride = ctx->item_super_stride;
+        CK(cudaMemsetAsync(ctx->lanes[lane].d_ctrl, 0, (2 * RR_MAX_PASSES + 1) * sizeof(uint32_t), ls));
+        if (Pn > 1) {
+            CK(cudaMemsetAsync(ctx->lanes[lane].d_item_start, 0, (size_t)(Pn + 1) * P.item_stride * sizeof(uint32_t), ls));
+            CK(cudaMemsetAsync(ctx->lanes[lane].d_super, 0, (size_t)(Pn + 1) * P.super_stride * sizeof(uint32_t), ls));
+            CK(cudaMemsetAsync(ctx->lanes[lane].d_item_super, 0, (size_t)(Pn + 1) * P.item_super_stride * sizeof(uint32_t), ls));
+        }
+        const uint32_t groups0 = (items * (uint32_t)P.n_samples + 31u) / 32u, warps_per_cta = RR_TRACE_BLOCK / 32;
+        const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)ctx->grid, (groups0 + warps_per_cta - 1) / warps_per_cta));
         const bool timed = ctx->tev_count < rr_ctx::kRing;
         cudaEvent_t* te = ctx->tev[timed ? ctx->tev_count : 0];
-        if (timed) CK(cudaEventRecord(te[0], st));
-        CK(rr_launch_trace(&P, std::max(grid, 1), st, stats, debug));
-        if (timed) CK(cudaEventRecord(te[1], st));
-        CK(rr_launch_draw(&P, (int)items, (size_t)P.n_cells * sizeof(float), st, debug));
-        if (timed) { CK(cudaEventRecord(te[2], st)); ctx->tev_count++; }
+        if (timed) CK(cudaEventRecord(te[0], ls));
+        for (int pass = 0; pass < Pn; pass++) {
+            /* later lists can be up to 2^pass times longer than list 0: keep the full persistent grid for them */
+            CK(rr_launch_trace(&P, pass, pass == 0 ? grid : ctx->grid, ls, stats, debug));
+            ctx->launches++;
+            if (pass + 1 < Pn) { CK(rr_launch_scan(&P, pass + 1, ls)); ctx->launches++; }
+        }
+        if (timed) CK(cudaEventRecord(te[1], ls));
+        CK(rr_launch_draw(&P, (int)items, (size_t)P.n_cells * sizeof(float), ls, debug));
+        ctx->launches++;
+        if (timed) { CK(cudaEventRecord(te[2], ls)); ctx->tev_count++; }
+        if (copy) {
+            CK(cudaMemcpyAsync(copy->h_dst + (size_t)first * out_stride, P.out, (size_t)n * out_stride, cudaMemcpyDeviceToHost, ls));
+            CK(cudaEventRecord(ctx->sub_ev[sub], ls));
+            copy->ranges.push_back(std::make_pair(first, n));
+        }
+    }
+    for (int l = 0; l < lanes_used; l++) {
+        CK(cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].stream));
+        CK(cudaStreamWaitEvent(st, ctx->lanes[l].done, 0));
     }
     P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0;
     return RR_OK;
@@ -597,8 +698,16 @@ static int collect(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
     s.kernel_ms = kernel_ms; s.bvh_build_ms = ctx->bvh_build_ms; s.overflow = flags[0];
     if (stats) *stats = s;
     if (flags[1]) return fail(ctx, RR_ERR_OUT_OF_RANGE, "a hit face carries an object id >= n_objects");
-    if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave/signal list overflow (cap %u waves per %d-sample chunk = %u per azimuth); raise rr_set_max_waves_per_azimuth", ctx->wave_cap, RR_CHUNK, ctx->wave_cap * ctx->n_chunks);
+    if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave list overflow (a pass produced more than %u waves per azimuth on average over a launch); raise rr_set_max_waves_per_azimuth", ctx->waves_per_item);
     return RR_OK;
+}
+
+/* true if cudaMemcpyAsync can write straight into `p` (page-locked by cudaHostAlloc / cudaHostRegister / torch pin_memory) */
+static bool host_ptr_is_pinned(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
 }
 
 static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int per_az, uint64_t frame_id0,
@@ -607,13 +716,16 @@ static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int
     int rc = ready(ctx);
     if (rc) return rc;
     if (!poses || !out_polar || n_frames == 0) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "simulate: NULL buffers or zero poses");
-    if ((rc = ensure_scratch(ctx, n_frames * RR_N_ANGLES))) return rc;
+    /* >= 4 sub-batches when there are enough poses: images of a finished sub-batch travel while the next one computes */
+    const int min_split = with_stats ? 1 : (int)std::min<size_t>(n_frames, 4);
+    if ((rc = ensure_scratch(ctx, ((n_frames + min_split - 1) / min_split) * RR_N_ANGLES))) return rc;
     const size_t n_pose_structs = n_frames * (per_az ? RR_N_ANGLES : 1);
     const size_t img = (size_t)ctx->cfg.n_cells * RR_N_ANGLES;
+    const bool direct = host_ptr_is_pinned(out_polar);
     CK(regrow(&ctx->d_poses, &ctx->d_poses_cap, n_pose_structs));
     CK(regrow(&ctx->d_out, &ctx->d_out_cap, n_frames * img));
     CK(regrow(&ctx->h_poses, &ctx->h_poses_cap, n_pose_structs, true));
-    CK(regrow(&ctx->h_out, &ctx->h_out_cap, n_frames * img, true));
+    if (!direct) CK(regrow(&ctx->h_out, &ctx->h_out_cap, n_frames * img, true));
     memcpy(ctx->h_poses, poses, n_pose_structs * sizeof(rr_pose));
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(ctx->d_poses, ctx->h_poses, n_pose_structs * sizeof(rr_pose), cudaMemcpyHostToDevice, st));
@@ -622,12 +734,16 @@ static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int
     P.poses = ctx->d_poses; P.n_poses = (int)n_frames; P.pose_per_azimuth = per_az;
     P.az_begin = 0; P.az_count = RR_N_ANGLES; P.frame_id0 = frame_id0;
     P.out = ctx->d_out; P.column_major = 0;
+    RRCopyOut copy;
+    copy.h_dst = direct ? out_polar : ctx->h_out;
     CK(cudaEventRecord(ctx->ev0, st));
-    if ((rc = enqueue(ctx, P, st, with_stats, 0))) return rc;
+    if ((rc = enqueue(ctx, P, st, with_stats, 0, min_split, &copy))) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
-    CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, n_frames * img, cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < copy.n_sub; k++) {               /* in order: hand every finished sub-batch to the caller */
+        CK(cudaEventSynchronize(ctx->sub_ev[k]));
+        if (!direct) memcpy(out_polar + (size_t)copy.ranges[k].first * img, ctx->h_out + (size_t)copy.ranges[k].first * img, (size_t)copy.ranges[k].second * img);
+    }
     CK(cudaStreamSynchronize(st));
-    memcpy(out_polar, ctx->h_out, n_frames * img);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     return collect(ctx, stats, ms);
@@ -658,7 +774,8 @@ int rr_simulate_device(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64
     if (!d_Tsm || !d_out_polar || n_poses == 0) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_device: NULL buffers or zero poses");
     if (azimuth_begin < 0 || azimuth_count < 1 || azimuth_begin + azimuth_count > RR_N_ANGLES)
         return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_device: azimuth shard [%d,%d) outside [0,400)", azimuth_begin, azimuth_begin + azimuth_count);
-    if ((rc = ensure_scratch(ctx, n_poses * (size_t)azimuth_count))) return rc;
+    const size_t nl = (size_t)std::max(1, std::min(ctx->n_lanes, (int)rr_ctx::kLanes));
+    if ((rc = ensure_scratch(ctx, ((n_poses + nl - 1) / nl) * (size_t)azimuth_count))) return rc;
     RRFrameParams P;
     fill_params(ctx, P);
     P.poses = d_Tsm; P.n_poses = (int)n_poses; P.pose_per_azimuth = pose_per_azimuth ? 1 : 0;
@@ -686,6 +803,14 @@ int rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_
     return RR_OK;
 }
 
+int rr_set_lanes(rr_ctx* ctx, int32_t n_lanes)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    if (n_lanes < 1 || n_lanes > rr_ctx::kLanes) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_lanes: 1..%d", (int)rr_ctx::kLanes);
+    ctx->n_lanes = n_lanes;
+    return RR_OK;
+}
+
 int rr_get_stats(rr_ctx* ctx, rr_stats* stats)
 {
     if (!ctx || !stats) return RR_ERR_INVALID_ARGUMENT;
@@ -703,53 +828,51 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
     if (rc) return rc;
     if (!Tsm) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_debug_trace: NULL pose");
     if ((rc = ensure_scratch(ctx, RR_N_ANGLES))) return rc;
-    const uint32_t Pn = std::max<uint32_t>(1, ctx->model.n_reflections);
-    const uint32_t ccap = ctx->wave_cap * Pn, scap = ctx->sig_cap;          /* per task */
-    const uint32_t n_chunks = ctx->n_chunks;
-    const size_t n_tasks = (size_t)RR_N_ANGLES * n_chunks;
+    const uint32_t Pn = std::max<uint32_t>(1, ctx->model.n_reflections), S = ctx->model.n_samples;
+    const size_t wcap = (((size_t)RR_N_ANGLES * ctx->waves_per_item) + 31) & ~(size_t)31;   /* = P.wave_cap of this launch */
+    const size_t istride = RR_N_ANGLES + 1;
     const int C = ctx->cfg.n_cells;
-    rr_cast_record* d_casts = nullptr; rr_signal_record* d_sigs = nullptr; uint32_t* d_cnt = nullptr; float* d_cols = nullptr;
+    rr_cast_record* d_casts = nullptr; rr_signal_record* d_sigs = nullptr; float* d_cols = nullptr;
     rr_pose* d_pose = nullptr; uint8_t* d_img = nullptr;
-    auto cleanup = [&]() { cudaFree(d_casts); cudaFree(d_sigs); cudaFree(d_cnt); cudaFree(d_cols); cudaFree(d_pose); cudaFree(d_img); };
+    auto cleanup = [&]() { cudaFree(d_casts); cudaFree(d_sigs); cudaFree(d_cols); cudaFree(d_pose); cudaFree(d_img); };
 #define CKD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
-    CKD(cudaMalloc((void**)&d_casts, n_tasks * ccap * sizeof(rr_cast_record)));
-    CKD(cudaMalloc((void**)&d_sigs, n_tasks * scap * sizeof(rr_signal_record)));
-    CKD(cudaMalloc((void**)&d_cnt, n_tasks * RR_MAX_PASSES * sizeof(uint32_t)));
+    CKD(cudaMalloc((void**)&d_casts, Pn * wcap * sizeof(rr_cast_record)));
+    CKD(cudaMalloc((void**)&d_sigs, 2 * Pn * wcap * sizeof(rr_signal_record)));
     CKD(cudaMalloc((void**)&d_cols, (size_t)RR_N_ANGLES * C * sizeof(float)));
     CKD(cudaMalloc((void**)&d_pose, sizeof(rr_pose)));
     CKD(cudaMalloc((void**)&d_img, (size_t)C * RR_N_ANGLES));
-    CKD(cudaMemset(d_cnt, 0, n_tasks * RR_MAX_PASSES * sizeof(uint32_t)));
     CKD(cudaMemcpy(d_pose, Tsm, sizeof(rr_pose), cudaMemcpyHostToDevice));
     RRFrameParams P;
     fill_params(ctx, P);
     P.poses = d_pose; P.n_poses = 1; P.pose_per_azimuth = 0; P.az_begin = 0; P.az_count = RR_N_ANGLES;
     P.frame_id0 = frame_id0; P.out = d_img; P.column_major = 0;
-    P.dbg_casts = d_casts; P.dbg_signals = d_sigs; P.dbg_counts = d_cnt; P.dbg_columns = d_cols;
-    P.dbg_cast_cap_w = ccap; P.dbg_sig_cap_w = scap;
+    P.dbg_casts = d_casts; P.dbg_signals = d_sigs; P.dbg_columns = d_cols;
     if ((rc = enqueue(ctx, P, ctx->stream, 1, 1))) { cleanup(); return rc; }
     CKD(cudaStreamSynchronize(ctx->stream));
-    /* re-assemble the reference's list order: for azimuth, for pass, for chunk: that chunk's (pass) segment */
-    std::vector<uint32_t> ccnt(n_tasks * RR_MAX_PASSES), scnt(n_tasks * RR_MAX_PASSES);
-    std::vector<rr_cast_record> hc(n_tasks * ccap);
-    std::vector<rr_signal_record> hs(n_tasks * scap);
-    CKD(cudaMemcpy(ccnt.data(), d_cnt, ccnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CKD(cudaMemcpy(scnt.data(), ctx->d_seg, scnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CKD(cudaMemcpy(hc.data(), d_casts, hc.size() * sizeof(rr_cast_record), cudaMemcpyDeviceToHost));
-    CKD(cudaMemcpy(hs.data(), d_sigs, hs.size() * sizeof(rr_signal_record), cudaMemcpyDeviceToHost));
+    /* the reference's list order: for azimuth, for pass: that azimuth's run of the pass list */
+    std::vector<uint32_t> totals(RR_MAX_PASSES + 1), starts((size_t)(Pn + 1) * istride);
+    CKD(cudaMemcpy(totals.data(), ctx->lanes[0].d_ctrl, totals.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(starts.data(), ctx->lanes[0].d_item_start, starts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     size_t nc = 0, ns = 0;
-    std::vector<uint32_t> coff(n_chunks), soff(n_chunks);
+    std::vector<rr_cast_record> hc; std::vector<rr_signal_record> hs;
+    if (casts) { hc.resize(Pn * wcap); CKD(cudaMemcpy(hc.data(), d_casts, hc.size() * sizeof(rr_cast_record), cudaMemcpyDeviceToHost)); }
+    hs.resize(2 * Pn * wcap);
+    CKD(cudaMemcpy(hs.data(), d_sigs, hs.size() * sizeof(rr_signal_record), cudaMemcpyDeviceToHost));
     for (int a = 0; a < RR_N_ANGLES; a++) {
-        std::fill(coff.begin(), coff.end(), 0u); std::fill(soff.begin(), soff.end(), 0u);
         for (uint32_t p = 0; p < ctx->model.n_reflections; p++) {
-            for (uint32_t w = 0; w < n_chunks; w++) {
-                const size_t task = (size_t)a * n_chunks + w;
-                const uint32_t c2 = ccnt[task * RR_MAX_PASSES + p], s2 = scnt[task * RR_MAX_PASSES + p];
-                for (uint32_t k = 0; k < c2; k++, nc++)
-                    if (casts && nc < cast_capacity && coff[w] + k < ccap) casts[nc] = hc[task * ccap + coff[w] + k];
-                for (uint32_t k = 0; k < s2; k++, ns++)
-                    if (signals && ns < signal_capacity && soff[w] + k < scap) signals[ns] = hs[task * scap + soff[w] + k];
-                coff[w] += c2; soff[w] += s2;
-            }
+            size_t b, e, lim;
+            if (p == 0) { b = (size_t)a * S; e = b + S; lim = (size_t)RR_N_ANGLES * S; }
+            else { b = starts[p * istride + a]; e = starts[p * istride + a + 1]; lim = std::min<size_t>(totals[p], wcap); }
+            b = std::min(b, lim); e = std::min(e, lim);
+            for (size_t j = b; j < e; j++, nc++)
+                if (casts && nc < cast_capacity) casts[nc] = hc[p * wcap + j];
+            for (size_t j = b; j < e; j++)
+                for (int k = 0; k < 2; k++) {
+                    const rr_signal_record& r = hs[2 * (p * wcap + j) + k];
+                    if (r.azimuth < 0) continue;
+                    if (signals && ns < signal_capacity) signals[ns] = r;
+                    ns++;
+                }
         }
     }
     if (n_casts) *n_casts = nc;

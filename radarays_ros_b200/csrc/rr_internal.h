@@ -43,10 +43,19 @@ struct RRBuildNode {
 #define RR_BLOCK 256
 #define RR_WARPS (RR_BLOCK / 32)
 #define RR_TRACE_BLOCK 128       /* trace kernel: 4 independent warps per CTA */
-#define RR_CHUNK 32              /* beam samples per trace task (= one warp) */
+#define RR_GROUP 32              /* waves per trace group (= one warp round) */
+#define RR_SCAN_BLOCK 1024       /* rr_scan_kernel: one CTA */
 #define RR_MAX_GRANULES 320      /* ceil(10000 cells / 32) rounded up */
 #define RR_MAX_PASSES 20         /* cfg/RadarModel.cfg:27 n_reflections <= 20 */
 
+/* Wavefront layout. The waves of pass p of ALL items (pose, azimuth) of a launch form ONE list in the reference's order
+ * (item-major; inside an item the order of RadarCPU.cpp:243,290,369). List p lives in wave buffer (p & 1). The trace
+ * kernel of pass p walks it in groups of 32 consecutive waves (one warp each) and appends the group's surviving
+ * children, compacted in order by ballot/popc, at slots [64 g, 64 g + count_g) of the other buffer; rr_scan_kernel
+ * turns the counts into the exclusive prefix group_base[] (+ first_src[]: for every group of the NEXT list the source
+ * group holding its first wave), so list position j of pass p+1 is slot 64 gg + (j - group_base[gg]) — no data is moved.
+ * Returns sit in per-wave slots [pass][j] (two per wave: path return, multipath return; cell == INT32_MIN = none), which
+ * IS the reference's signal order. item_start[p][item] = first list position of the item's waves in pass p. */
 struct RRFrameParams {
     /* scene */
     const RRNode* nodes;
@@ -62,6 +71,7 @@ struct RRFrameParams {
     const rr_pose* poses;          /* n_poses (or n_poses*400 when pose_per_azimuth) */
     int32_t n_samples, n_passes, n_poses, pose_per_azimuth;
     int32_t az_begin, az_count;
+    int32_t n_items;               /* n_poses * az_count */
     /* image formation */
     int32_t n_cells, scroll_image;
     double resolution;
@@ -77,27 +87,32 @@ struct RRFrameParams {
     /* output */
     uint8_t* out;                  /* row-major [pose][cell][400] or column-major [pose][az-az_begin][cell] */
     int32_t column_major;
-    /* per-resident-warp scratch of the trace kernel (SoA so that lanes access consecutive words) */
-    float* wave_f32;               /* [warp][2 lists][6 comps][wave_cap_w] orig.xyz dir.xyz */
-    double* wave_f64;              /* [warp][2 lists][2 comps][wave_cap_w] energy, time */
-    uint32_t* wave_mat;            /* [warp][2 lists][wave_cap_w] material id */
-    /* per-task output of the trace kernel; task = (pose, azimuth, chunk of RR_CHUNK samples) */
-    int32_t* sig_cell;             /* [task][sig_cap_w] returns in generation order (pass 0 first) */
-    float* sig_strength;           /* [task][sig_cap_w] */
-    uint32_t* seg_counts;          /* [task][RR_MAX_PASSES] returns emitted in each pass */
-    uint32_t* item_pass_waves;     /* [item][RR_MAX_PASSES] waves traced per pass (stats: max list length) */
-    uint32_t wave_cap_w, sig_cap_w;
-    int32_t n_chunks;              /* ceil(n_samples / RR_CHUNK) */
+    /* wave lists (SoA over slots so that lanes access consecutive words) */
+    float* wave_f32;               /* [2 buffers][6 comps][slot_cap] orig.xyz dir.xyz */
+    double* wave_f64;              /* [2 buffers][2 comps][slot_cap] energy, time */
+    uint32_t* wave_mat;            /* [2 buffers][slot_cap] material id */
+    uint32_t* wave_item;           /* [2 buffers][slot_cap] item = pose * az_count + (azimuth - az_begin) */
+    uint32_t wave_cap;             /* longest pass list a launch can hold (multiple of 32) */
+    uint32_t slot_cap;             /* 2 * wave_cap */
+    uint32_t group_cap;            /* wave_cap / 32 */
+    uint32_t* group_base;          /* [2 buffers][group_cap + 1] child counts, then their exclusive prefix (+ total) */
+    uint32_t* first_src;           /* [group_cap + 1] source group of wave 32 g of the current list */
+    uint32_t* pass_total;          /* [RR_MAX_PASSES + 1] list length of pass p (p >= 1; pass 0 = n_items * n_samples) */
+    uint32_t* item_start;          /* [n_passes + 1][item_stride] per-item child counts, then exclusive prefix (+ total) */
+    uint32_t item_stride;
+    uint32_t* super_count;         /* [n_passes + 1][super_stride] child count of every 1024 consecutive groups of a pass */
+    uint32_t* item_super;          /* [n_passes + 1][item_super_stride] idem for every 1024 consecutive items */
+    uint32_t super_stride, item_super_stride;
+    int2* sig_cell;                /* [n_passes][wave_cap] range cells of the (path, multipath) return of wave j */
+    float2* sig_strength;          /* [n_passes][wave_cap] */
     /* control + counters */
-    uint32_t* work_counter;
+    uint32_t* work_counter;        /* [RR_MAX_PASSES] next group of pass p */
     unsigned long long* counters;  /* [0] casts [1] hits [2] signals [3] nodes [4] tris [5] max_waves */
     int32_t* error_flags;          /* [0] wave overflow [1] object/material id out of range */
     /* debug (rr_debug_trace) */
-    rr_cast_record* dbg_casts;     /* [task][dbg_cast_cap_w], per task in (pass, list) order */
-    rr_signal_record* dbg_signals; /* [task][dbg_sig_cap_w] */
-    uint32_t* dbg_counts;          /* [task][RR_MAX_PASSES] casts of that (task, pass) segment */
+    rr_cast_record* dbg_casts;     /* [n_passes][wave_cap] */
+    rr_signal_record* dbg_signals; /* [n_passes][wave_cap][2] */
     float* dbg_columns;            /* [az][cell] */
-    uint32_t dbg_cast_cap_w, dbg_sig_cap_w;
 };
 
 #endif

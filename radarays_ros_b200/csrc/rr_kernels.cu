@@ -1,10 +1,11 @@
 /* rr_kernels.cu — sm_100a kernels of the RadaRays hot path (RadarCPU::simulate, RadarCPU.cpp:30-564).
  *
- * rr_trace_kernel (persistent, barrier-free, one WARP per 32-sample chunk task):
+ * rr_trace_kernel, once per pass (persistent, barrier-free, one WARP per group of 32 waves of the launch-wide list):
  *   beam bundle generation      (RadarCPU.cpp:184-209, radar_algorithms.cpp:150-169)
  *   closest-hit traversal       (Rmagine/Embree call at RadarCPU.cpp:236) over the 32-byte quantised BVH
  *   move + Snell/Fresnel + BRDF (radar_types.h:108-120, radar_algorithms.h:55-139,168-187, RadarCPU.cpp:243-371)
  *   pruning + ordered respawn   (RadarCPU.cpp:288-290,364-389) via ballot/popc compaction (keeps the reference's list order)
+ * rr_scan_kernel between passes: prefix sums that turn per-group child counts into the next pass's list (no data moved)
  * rr_draw_kernel (one CTA per (pose, azimuth)):
  *   range-bin accumulation      (RadarCPU.cpp:402-450) into a shared-memory column, in reference order, no atomics
  *   energy_max / ambient noise / normalise / mono8 (RadarCPU.cpp:453-542)
@@ -182,278 +183,258 @@ __device__ __forceinline__ uint8_t rr_to_u8(float v)
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Kernel 1/2: rr_trace_kernel — beam rays -> multi-bounce closest hit -> Snell/Fresnel + BRDF -> returns.
+ * Kernel 1/3: rr_trace_kernel — ONE PASS of all items: wave -> closest hit -> Snell/Fresnel + BRDF -> returns, children.
  *
- * Persistent, barrier-free: every WARP is an independent worker pulling (pose, azimuth, chunk) tasks from a global
- * counter; a chunk is 32 consecutive beam samples and the warp walks that chunk's wave tree through all passes on
- * its own (ballot/popc compaction into the warp's ping-pong lists, no block barrier, no shared memory). The
- * reference's list order (RadarCPU.cpp:243,290,322,369: pass-major, parents in order, reflection before refraction)
- * is kept because by induction every chunk's waves form one contiguous run of each pass's list: the canonical order is
- * "for pass: for chunk: that chunk's (pass) segment", which rr_draw_kernel replays from the per-task segment counts.
+ * Wavefront over the whole launch (rr_internal.h): the pass's wave list is cut into groups of 32 consecutive waves; a
+ * persistent grid of independent warps pulls groups from a global counter, so every warp round runs 32 live waves
+ * whatever the per-azimuth list lengths are (a per-azimuth or per-chunk loop leaves a third of the lanes idle after
+ * pass 0). A group appends its surviving children in the reference's order (RadarCPU.cpp:243,290,369: parents in list
+ * order, reflection before refraction) by ballot/popc compaction into its own 64 slots; no barrier, no shared memory.
  * ---------------------------------------------------------------------------------------------- */
 template <bool STATS, bool DEBUG>
-__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel(const RRFrameParams P)
+__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel(const RRFrameParams P, const int pass)
 {
     const int lane = threadIdx.x & 31;
-    const int warp_in_block = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t cap = P.wave_cap_w, scap = P.sig_cap_w;
-    const size_t wslot = (size_t)blockIdx.x * (RR_TRACE_BLOCK / 32) + warp_in_block;
-    float* wf = P.wave_f32 + wslot * 2 * 6 * cap;
-    double* wd = P.wave_f64 + wslot * 2 * 2 * cap;
-    uint32_t* wm = P.wave_mat + wslot * 2 * cap;
-    const int n_passes = P.n_passes;
-    const uint32_t n_chunks = (uint32_t)P.n_chunks;
-    const uint32_t total_tasks = (uint32_t)P.n_poses * (uint32_t)P.az_count * n_chunks;
+    const uint32_t S = (uint32_t)P.n_samples;
+    const uint32_t n_in = (pass == 0) ? (uint32_t)P.n_items * S : min(P.pass_total[pass], P.wave_cap);
+    const uint32_t n_groups = (n_in + 31u) >> 5;
+    const bool last_pass = (pass == P.n_passes - 1);
+    const size_t sc = P.slot_cap;
+    const int ib = pass & 1, ob = ib ^ 1;
+    const float* cf = P.wave_f32 + (size_t)ib * 6 * sc;
+    const double* cd = P.wave_f64 + (size_t)ib * 2 * sc;
+    const uint32_t* cm = P.wave_mat + (size_t)ib * sc;
+    const uint32_t* ci = P.wave_item + (size_t)ib * sc;
+    float* nf = P.wave_f32 + (size_t)ob * 6 * sc;
+    double* ndp = P.wave_f64 + (size_t)ob * 2 * sc;
+    uint32_t* nm = P.wave_mat + (size_t)ob * sc;
+    uint32_t* ni = P.wave_item + (size_t)ob * sc;
+    const uint32_t* gbase = P.group_base + (size_t)ib * (P.group_cap + 1);
+    uint32_t* gcount = P.group_base + (size_t)ob * (P.group_cap + 1);
+    uint32_t* item_count_next = P.item_start + (size_t)(pass + 1) * P.item_stride;
+    uint32_t* super_next = P.super_count + (size_t)(pass + 1) * P.super_stride;
+    uint32_t* item_super_next = P.item_super + (size_t)(pass + 1) * P.item_super_stride;
+    int2* sg_cell = P.sig_cell + (size_t)pass * P.wave_cap;
+    float2* sg_str = P.sig_strength + (size_t)pass * P.wave_cap;
     const float go[3] = {P.grid_origin[0], P.grid_origin[1], P.grid_origin[2]};
     const float gs[3] = {P.grid_scale[0], P.grid_scale[1], P.grid_scale[2]};
     unsigned stat_nodes = 0, stat_tris = 0;
+    uint32_t warp_casts = 0, warp_hits = 0, warp_sigs = 0;
 
     while (true) {
-        uint32_t task = 0;
-        if (lane == 0) task = atomicAdd(P.work_counter, 1u);
-        task = __shfl_sync(RR_FULL, task, 0);
-        if (task >= total_tasks) break;
-        const uint32_t item = task / n_chunks, chunk = task % n_chunks;
-        const int pose_i = (int)(item / (uint32_t)P.az_count);
-        const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
-        const uint32_t s_begin = chunk * 32u;
-        const uint32_t s_count = min((uint32_t)P.n_samples - s_begin, 32u);
-        int32_t* sg_cell = P.sig_cell + (size_t)task * scap;
-        float* sg_str = P.sig_strength + (size_t)task * scap;
-        uint32_t* seg = P.seg_counts + (size_t)task * RR_MAX_PASSES;
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(P.work_counter + pass, 1u);
+        g = __shfl_sync(RR_FULL, g, 0);
+        if (g >= n_groups) break;
+        const uint32_t j = g * 32u + (uint32_t)lane;
+        const bool active = j < n_in;
 
-        /* Tam = Tsm * Tas (RadarCPU.cpp:201-206); Tas.t = 0 */
-        const rr_pose ps = P.poses[P.pose_per_azimuth ? (pose_i * RR_N_ANGLES + az) : pose_i];
-        rr_quat Rsm; Rsm.x = ps.qx; Rsm.y = ps.qy; Rsm.z = ps.qz; Rsm.w = ps.qw;
-        const float4 tq = P.tas_quat[az];
-        rr_quat Ras; Ras.x = tq.x; Ras.y = tq.y; Ras.z = tq.z; Ras.w = tq.w;
-        const rr_quat R = rr_qmul(Rsm, Ras);
-        const rr_quat Rinv = rr_qinv(R);
-        const rr_vec3 T = rr_add(rr_qrot(Rsm, rr_v3(0.f, 0.f, 0.f)), rr_v3(ps.tx, ps.ty, ps.tz));
+        uint32_t item = 0;
+        bool keep0 = false, keep1 = false, hit = false;
+        uint32_t n_child = 0, n_sig = 0;
+        rr_vec3 c_o = rr_v3(0, 0, 0), c_d0 = c_o, c_d1 = c_o;
+        double c_time = 0, c_e0 = 0, c_e1 = 0;
+        uint32_t c_m0 = 0, c_m1 = 0;
+        int sig_cell0 = INT32_MIN, sig_cell1 = INT32_MIN;
+        float sig_s0 = 0, sig_s1 = 0, sig_t0 = 0, sig_t1 = 0;
+        int face = -1, az = 0; float range = 0.f; float dbg_energy = 0.f;
 
-        uint32_t n_cur = s_count;
-        int cur = 0;
-        uint32_t sig_off = 0, warp_hits = 0, warp_casts = 0;
+        if (active) {
+            RRWave w;
+            if (pass == 0) {                              /* RadarCPU.cpp:106-114,184 */
+                item = j / S;
+                const uint32_t smp = j - item * S;
+                w.o = rr_v3(0.f, 0.f, 0.f);
+                w.d = rr_v3(P.beam_dirs[3 * smp], P.beam_dirs[3 * smp + 1], P.beam_dirs[3 * smp + 2]);
+                w.energy = 1.0; w.time = 0.0; w.mat = 0u;
+            } else {                                      /* list position j -> slot (rr_internal.h) */
+                uint32_t gg = P.first_src[g];
+                while (gbase[gg + 1] <= j) gg++;
+                const size_t slot = (size_t)gg * 64u + (j - gbase[gg]);
+                w.o = rr_v3(cf[0 * sc + slot], cf[1 * sc + slot], cf[2 * sc + slot]);
+                w.d = rr_v3(cf[3 * sc + slot], cf[4 * sc + slot], cf[5 * sc + slot]);
+                w.energy = cd[0 * sc + slot]; w.time = cd[1 * sc + slot];
+                w.mat = cm[slot];
+                item = ci[slot];
+            }
+            dbg_energy = (float)w.energy;
+            /* Tam = Tsm * Tas (RadarCPU.cpp:201-206); Tas.t = 0 */
+            const int pose_i = (int)(item / (uint32_t)P.az_count);
+            az = P.az_begin + (int)(item % (uint32_t)P.az_count);
+            const rr_pose ps = P.poses[P.pose_per_azimuth ? (pose_i * RR_N_ANGLES + az) : pose_i];
+            rr_quat Rsm; Rsm.x = ps.qx; Rsm.y = ps.qy; Rsm.z = ps.qz; Rsm.w = ps.qw;
+            const float4 tq = P.tas_quat[az];
+            rr_quat Ras; Ras.x = tq.x; Ras.y = tq.y; Ras.z = tq.z; Ras.w = tq.w;
+            const rr_quat R = rr_qmul(Rsm, Ras);
+            const rr_vec3 T = rr_add(rr_qrot(Rsm, rr_v3(0.f, 0.f, 0.f)), rr_v3(ps.tx, ps.ty, ps.tz));
+            /* ray into the map frame; closest hit within [0, 1000] m (radar_algorithms.cpp:157-158) */
+            const rr_vec3 o_m = rr_add(rr_qrot(R, w.o), T);
+            const rr_vec3 d_m = rr_qrot(R, w.d);
+            const int slot_t = rr_trace<STATS>(P.nodes, P.tris, P.root_ref, go, gs, o_m, d_m, 1000.0f,
+                                               range, face, stat_nodes, stat_tris);
+            if (slot_t >= 0) {
+                const float4 q1 = __ldg(P.tris + 3 * slot_t + 1);
+                const float4 q2 = __ldg(P.tris + 3 * slot_t + 2);
+                const uint32_t obj = __float_as_uint(q1.w);
+                if (obj >= (uint32_t)P.n_objects) {
+                    atomicExch(&P.error_flags[1], 1);
+                } else {
+                    hit = true;
+                    /* geometric normal -> ray frame, facing the ray, re-normalised (RadarCPU.cpp:248) */
+                    rr_vec3 n = rr_normalize(rr_cross(rr_v3(q1.x, q1.y, q1.z), rr_v3(q2.x, q2.y, q2.z)));
+                    n = rr_qrot(rr_qinv(R), n);
+                    if (rr_dot(w.d, n) > 0.0f) n = rr_neg(n);
+                    n = rr_normalize(n);
 
-        for (int pass = 0; pass < n_passes; pass++) {
-            const bool last_pass = (pass == n_passes - 1);
-            const float* cf = wf + (size_t)cur * 6 * cap;
-            const double* cd = wd + (size_t)cur * 2 * cap;
-            const uint32_t* cm = wm + (size_t)cur * cap;
-            float* nf = wf + (size_t)(cur ^ 1) * 6 * cap;
-            double* ndp = wd + (size_t)(cur ^ 1) * 2 * cap;
-            uint32_t* nm = wm + (size_t)(cur ^ 1) * cap;
-            const uint32_t seg_start = sig_off;
-            uint32_t next_n = 0;
+                    /* move to the surface (radar_types.h:108-113) */
+                    const rr_vec3 p_hit = rr_add(w.o, rr_muls(w.d, range));
+                    const double wave_v = RR_WAVE_VELOCITY;
+                    const double t_hit = w.time + (double)range / wave_v;
 
-            for (uint32_t base = 0; base < n_cur; base += 32) {
-                const uint32_t i = base + lane;
-                const bool active = i < n_cur;
-                uint32_t n_child = 0, n_sig = 0;
-                rr_vec3 c_o = rr_v3(0, 0, 0), c_d0 = c_o, c_d1 = c_o;
-                double c_time = 0, c_e0 = 0, c_e1 = 0;
-                uint32_t c_m0 = 0, c_m1 = 0;
-                bool keep0 = false, keep1 = false;
-                int sig_cell0 = 0, sig_cell1 = 0;
-                float sig_s0 = 0, sig_s1 = 0, sig_t0 = 0, sig_t1 = 0;
-                bool hit = false;
-                int face = -1; float range = 0.f; float dbg_energy = 0.f;
+                    /* medium on the far side (RadarCPU.cpp:266-280) */
+                    const uint32_t air = (uint32_t)P.material_id_air;
+                    const uint32_t mat_t = (w.mat == air) ? (uint32_t)P.object_materials[obj] : air;
+                    const float4 mt = P.materials[mat_t];
+                    const float v_t = (w.mat != mat_t) ? mt.x : (float)wave_v;
 
-                if (active) {
-                    RRWave w;
-                    if (pass == 0) {                      /* RadarCPU.cpp:106-114,184 */
-                        const uint32_t smp = s_begin + i;
-                        w.o = rr_v3(0.f, 0.f, 0.f);
-                        w.d = rr_v3(P.beam_dirs[3 * smp], P.beam_dirs[3 * smp + 1], P.beam_dirs[3 * smp + 2]);
-                        w.energy = 1.0; w.time = 0.0; w.mat = 0u;
+                    /* Snell/Fresnel (radar_algorithms.h:55-139): n1 := v2, n2 := v1 */
+                    const double n1 = (double)v_t, n2 = wave_v;
+                    const float cos_i = rr_dot(rr_neg(w.d), n);
+                    const float th_if = rr_acosf(cos_i);
+                    const double th_i = (double)th_if;
+                    const rr_vec3 d_refl = rr_add(w.d, rr_muls(rr_muls(n, 2.0f), rr_dot(rr_neg(n), w.d)));
+                    rr_vec3 d_refr = rr_v3(0.f, 0.f, 0.f);
+                    rr_vec3 nn = n;
+                    if (n1 > 0.0) {
+                        const double n21 = n2 / n1;
+                        double th_limit = 100.0;
+                        if (fabs(n21) <= 1.0) th_limit = rr_asin(n21);
+                        if (th_i <= th_limit) {
+                            if (rr_dot(nn, w.d) > 0.0f) nn = rr_neg(nn);
+                            if (n2 > 0.0) {
+                                const double n12 = n1 / n2;
+                                const double c = rr_cos(th_i);
+                                const double k = n12 * c - sqrt(1 - n12 * n12 * (1 - c * c));
+                                d_refr = rr_add(rr_muls(w.d, (float)n12), rr_muls(nn, (float)k));
+                            }
+                        }
+                    }
+                    const double th_t = (double)rr_acosf(rr_dot(d_refr, rr_neg(nn)));
+                    double rs, rp;
+                    const double th_sum = th_i + th_t;
+                    if (th_sum < 0.0001) {
+                        rs = (n1 - n2) / (n1 + n2); rp = rs;
+                    } else if (th_sum > M_PI - 0.0001) {
+                        rs = 1.0; rp = 1.0;
                     } else {
-                        w.o = rr_v3(cf[0 * cap + i], cf[1 * cap + i], cf[2 * cap + i]);
-                        w.d = rr_v3(cf[3 * cap + i], cf[4 * cap + i], cf[5 * cap + i]);
-                        w.energy = cd[0 * cap + i]; w.time = cd[1 * cap + i];
-                        w.mat = cm[i];
+                        const rr_sincos_t pd = rr_sincos_parts(th_i - th_t), psum = rr_sincos_parts(th_sum);
+                        rs = -rr_sin_of(pd) / rr_sin_of(psum);
+                        rp = rr_tan_of(pd) / rr_tan_of(psum);
                     }
-                    dbg_energy = (float)w.energy;
-                    /* ray into the map frame; closest hit within [0, 1000] m (radar_algorithms.cpp:157-158) */
-                    const rr_vec3 o_m = rr_add(rr_qrot(R, w.o), T);
-                    const rr_vec3 d_m = rr_qrot(R, w.d);
-                    const int slot = rr_trace<STATS>(P.nodes, P.tris, P.root_ref, go, gs, o_m, d_m, 1000.0f,
-                                                     range, face, stat_nodes, stat_tris);
-                    if (slot >= 0) {
-                        const float4 q1 = __ldg(P.tris + 3 * slot + 1);
-                        const float4 q2 = __ldg(P.tris + 3 * slot + 2);
-                        const uint32_t obj = __float_as_uint(q1.w);
-                        if (obj >= (uint32_t)P.n_objects) {
-                            atomicExch(&P.error_flags[1], 1);
-                        } else {
-                            hit = true;
-                            /* geometric normal -> ray frame, facing the ray, re-normalised (RadarCPU.cpp:248) */
-                            rr_vec3 n = rr_normalize(rr_cross(rr_v3(q1.x, q1.y, q1.z), rr_v3(q2.x, q2.y, q2.z)));
-                            n = rr_qrot(Rinv, n);
-                            if (rr_dot(w.d, n) > 0.0f) n = rr_neg(n);
-                            n = rr_normalize(n);
+                    const double Reff = 0.5 * (rs * rs) + (1.0 - 0.5) * (rp * rp);
+                    const double Teff = 1.0 - Reff;
+                    const double e_refl = Reff * w.energy;
+                    const double e_refr = Teff * w.energy;
+                    const double thr = (double)0.001f;                 /* Radar.cpp:24 */
 
-                            /* move to the surface (radar_types.h:108-113) */
-                            const rr_vec3 p_hit = rr_add(w.o, rr_muls(w.d, range));
-                            const double wave_v = RR_WAVE_VELOCITY;
-                            const double t_hit = w.time + (double)range / wave_v;
-
-                            /* medium on the far side (RadarCPU.cpp:266-280) */
-                            const uint32_t air = (uint32_t)P.material_id_air;
-                            const uint32_t mat_t = (w.mat == air) ? (uint32_t)P.object_materials[obj] : air;
-                            const float4 mt = P.materials[mat_t];
-                            const float v_t = (w.mat != mat_t) ? mt.x : (float)wave_v;
-
-                            /* Snell/Fresnel (radar_algorithms.h:55-139): n1 := v2, n2 := v1 */
-                            const double n1 = (double)v_t, n2 = wave_v;
-                            const float cos_i = rr_dot(rr_neg(w.d), n);
-                            const float th_if = rr_acosf(cos_i);
-                            const double th_i = (double)th_if;
-                            const rr_vec3 d_refl = rr_add(w.d, rr_muls(rr_muls(n, 2.0f), rr_dot(rr_neg(n), w.d)));
-                            rr_vec3 d_refr = rr_v3(0.f, 0.f, 0.f);
-                            rr_vec3 nn = n;
-                            if (n1 > 0.0) {
-                                const double n21 = n2 / n1;
-                                double th_limit = 100.0;
-                                if (fabs(n21) <= 1.0) th_limit = rr_asin(n21);
-                                if (th_i <= th_limit) {
-                                    if (rr_dot(nn, w.d) > 0.0f) nn = rr_neg(nn);
-                                    if (n2 > 0.0) {
-                                        const double n12 = n1 / n2;
-                                        const double c = rr_cos(th_i);
-                                        const double k = n12 * c - sqrt(1 - n12 * n12 * (1 - c * c));
-                                        d_refr = rr_add(rr_muls(w.d, (float)n12), rr_muls(nn, (float)k));
-                                    }
+                    c_o = p_hit; c_time = t_hit;
+                    if (e_refl > thr) {                                /* RadarCPU.cpp:288 */
+                        keep0 = true; c_d0 = d_refl; c_e0 = e_refl; c_m0 = w.mat;
+                        if (w.mat == air) {                            /* :302 — return to the sensor */
+                            const float e_f = (float)e_refl;
+                            {   /* BRDF, radar_algorithms.h:168-187: (A, B, C) = (ambient, diffuse, specular) */
+                                const float lobe = rr_powf(rr_cosf(th_if), mt.w);
+                                const float total = mt.y * 1.0f + mt.z * lobe;
+                                const float ret = total * e_f;
+                                if (pass == 0 || P.record_multi_reflection) {
+                                    const float t_back = (float)(t_hit * 2.0);
+                                    sig_cell0 = rr_signal_cell((double)t_back, P.resolution);
+                                    sig_s0 = ret; sig_t0 = t_back; n_sig = 1;
                                 }
                             }
-                            const double th_t = (double)rr_acosf(rr_dot(d_refr, rr_neg(nn)));
-                            double rs, rp;
-                            const double th_sum = th_i + th_t;
-                            if (th_sum < 0.0001) {
-                                rs = (n1 - n2) / (n1 + n2); rp = rs;
-                            } else if (th_sum > M_PI - 0.0001) {
-                                rs = 1.0; rp = 1.0;
-                            } else {
-                                const rr_sincos_t pd = rr_sincos_parts(th_i - th_t), psum = rr_sincos_parts(th_sum);
-                                rs = -rr_sin_of(pd) / rr_sin_of(psum);
-                                rp = rr_tan_of(pd) / rr_tan_of(psum);
-                            }
-                            const double Reff = 0.5 * (rs * rs) + (1.0 - 0.5) * (rp * rp);
-                            const double Teff = 1.0 - Reff;
-                            const double e_refl = Reff * w.energy;
-                            const double e_refr = Teff * w.energy;
-                            const double thr = (double)0.001f;                 /* Radar.cpp:24 */
-
-                            c_o = p_hit; c_time = t_hit;
-                            if (e_refl > thr) {                                /* RadarCPU.cpp:288 */
-                                keep0 = true; c_d0 = d_refl; c_e0 = e_refl; c_m0 = w.mat;
-                                if (w.mat == air) {                            /* :302 — return to the sensor */
-                                    const float e_f = (float)e_refl;
-                                    {   /* BRDF, radar_algorithms.h:168-187: (A, B, C) = (ambient, diffuse, specular) */
-                                        const float lobe = rr_powf(rr_cosf(th_if), mt.w);
-                                        const float total = mt.y * 1.0f + mt.z * lobe;
-                                        const float ret = total * e_f;
-                                        if (pass == 0 || P.record_multi_reflection) {
-                                            const float t_back = (float)(t_hit * 2.0);
-                                            sig_cell0 = rr_signal_cell((double)t_back, P.resolution);
-                                            sig_s0 = ret; sig_t0 = t_back; n_sig = 1;
-                                        }
-                                    }
-                                    if (pass > 0 && P.record_multi_path) {     /* :325-360 */
-                                        const float dist_f = rr_l2norm(p_hit);
-                                        const rr_vec3 to_hit = rr_divs(p_hit, rr_l2norm(p_hit));
-                                        const double t_sensor = (double)dist_f / wave_v;
-                                        const double view = (double)rr_dot(w.d, to_hit);
-                                        const float ang = rr_acosf(rr_dot(rr_neg(d_refl), to_hit));
-                                        if (view > P.multipath_threshold) {
-                                            const float lobe = rr_powf(rr_cosf(ang), mt.w);
-                                            const float total = mt.y * 1.0f + mt.z * lobe;
-                                            const float ret = total * e_f;
-                                            const double t_air = t_hit + t_sensor;
-                                            const int cell = rr_signal_cell(t_air, P.resolution);
-                                            if (n_sig == 0) { sig_cell0 = cell; sig_s0 = ret; sig_t0 = (float)t_air; }
-                                            else { sig_cell1 = cell; sig_s1 = ret; sig_t1 = (float)t_air; }
-                                            n_sig++;
-                                        }
-                                    }
+                            if (pass > 0 && P.record_multi_path) {     /* :325-360 */
+                                const float dist_f = rr_l2norm(p_hit);
+                                const rr_vec3 to_hit = rr_divs(p_hit, rr_l2norm(p_hit));
+                                const double t_sensor = (double)dist_f / wave_v;
+                                const double view = (double)rr_dot(w.d, to_hit);
+                                const float ang = rr_acosf(rr_dot(rr_neg(d_refl), to_hit));
+                                if (view > P.multipath_threshold) {
+                                    const float lobe = rr_powf(rr_cosf(ang), mt.w);
+                                    const float total = mt.y * 1.0f + mt.z * lobe;
+                                    const float ret = total * e_f;
+                                    const double t_air = t_hit + t_sensor;
+                                    const int cell = rr_signal_cell(t_air, P.resolution);
+                                    if (n_sig == 0) { sig_cell0 = cell; sig_s0 = ret; sig_t0 = (float)t_air; }
+                                    else { sig_cell1 = cell; sig_s1 = ret; sig_t1 = (float)t_air; }
+                                    n_sig++;
                                 }
                             }
-                            if (e_refr > thr) {                                /* :364-370 */
-                                keep1 = true; c_d1 = d_refr; c_e1 = e_refr; c_m1 = mat_t;
-                            }
-                            n_child = (keep0 ? 1u : 0u) + (keep1 ? 1u : 0u);
                         }
                     }
+                    if (e_refr > thr) {                                /* :364-370 */
+                        keep1 = true; c_d1 = d_refr; c_e1 = e_refr; c_m1 = mat_t;
+                    }
+                    n_child = (keep0 ? 1u : 0u) + (keep1 ? 1u : 0u);
                 }
+            }
+            /* returns of wave j, in the order RadarCPU.cpp:322,358 appends them; a slot without a return (and a return
+             * whose time is not a number, which can not reach a bin either) carries cell INT32_MIN */
+            sg_cell[j] = make_int2((n_sig >= 1) ? sig_cell0 : INT32_MIN, (n_sig >= 2) ? sig_cell1 : INT32_MIN);
+            if (n_sig) sg_str[j] = make_float2(sig_s0, sig_s1);
+            if (DEBUG) {
+                const size_t r0 = (size_t)pass * P.wave_cap + j;
+                rr_cast_record r; r.azimuth = az; r.pass = pass; r.face_id = hit ? face : -1;
+                r.range = hit ? range : 0.f; r.energy = dbg_energy; r.n_children = (int)n_child;
+                P.dbg_casts[r0] = r;
+                rr_signal_record s0; s0.azimuth = (n_sig >= 1) ? az : -1; s0.cell = sig_cell0; s0.strength = sig_s0; s0.time = sig_t0;
+                rr_signal_record s1; s1.azimuth = (n_sig >= 2) ? az : -1; s1.cell = sig_cell1; s1.strength = sig_s1; s1.time = sig_t1;
+                P.dbg_signals[2 * r0] = s0; P.dbg_signals[2 * r0 + 1] = s1;
+            }
+        }
 
-                /* ordered compaction inside the warp (reflection before refraction, parents in list order).
-                 * The reference also builds waves_new in its last pass and drops it (RadarCPU.cpp:380-389):
-                 * nothing traces those waves, so the last pass appends none (n_children is still reported). */
-                if (last_pass) { keep0 = false; keep1 = false; }
-                const uint32_t m0 = __ballot_sync(RR_FULL, keep0), m1 = __ballot_sync(RR_FULL, keep1);
-                const uint32_t ms0 = __ballot_sync(RR_FULL, n_sig >= 1), ms1 = __ballot_sync(RR_FULL, n_sig >= 2);
-                warp_hits += __popc(__ballot_sync(RR_FULL, hit));
-                uint32_t co = next_n + __popc(m0 & lt_mask) + __popc(m1 & lt_mask);
-                const uint32_t so = sig_off + __popc(ms0 & lt_mask) + __popc(ms1 & lt_mask);
-                const float skip = 0.001f;                                     /* RadarCPU.cpp:374-378 */
-                if (keep0) {
-                    if (co < cap) {
-                        const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d0, skip));
-                        nf[0 * cap + co] = o2.x; nf[1 * cap + co] = o2.y; nf[2 * cap + co] = o2.z;
-                        nf[3 * cap + co] = c_d0.x; nf[4 * cap + co] = c_d0.y; nf[5 * cap + co] = c_d0.z;
-                        ndp[0 * cap + co] = c_e0; ndp[1 * cap + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
-                        nm[co] = c_m0;
-                    }
-                    co++;
-                }
-                if (keep1) {
-                    if (co < cap) {
-                        const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d1, skip));
-                        nf[0 * cap + co] = o2.x; nf[1 * cap + co] = o2.y; nf[2 * cap + co] = o2.z;
-                        nf[3 * cap + co] = c_d1.x; nf[4 * cap + co] = c_d1.y; nf[5 * cap + co] = c_d1.z;
-                        ndp[0 * cap + co] = c_e1; ndp[1 * cap + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
-                        nm[co] = c_m1;
-                    }
-                }
-                if (n_sig > 0) {
-                    if (so < scap) { sg_cell[so] = sig_cell0; sg_str[so] = sig_s0; }
-                    if (n_sig > 1 && so + 1 < scap) { sg_cell[so + 1] = sig_cell1; sg_str[so + 1] = sig_s1; }
-                    if (DEBUG) {
-                        rr_signal_record* ds = P.dbg_signals + (size_t)task * P.dbg_sig_cap_w;
-                        if (so < P.dbg_sig_cap_w) {
-                            rr_signal_record r; r.azimuth = az; r.cell = sig_cell0; r.strength = sig_s0; r.time = sig_t0;
-                            ds[so] = r;
-                        }
-                        if (n_sig > 1 && so + 1 < P.dbg_sig_cap_w) {
-                            rr_signal_record r; r.azimuth = az; r.cell = sig_cell1; r.strength = sig_s1; r.time = sig_t1;
-                            ds[so + 1] = r;
-                        }
-                    }
-                }
-                if (DEBUG && active && warp_casts + i < P.dbg_cast_cap_w) {
-                    rr_cast_record r; r.azimuth = az; r.pass = pass; r.face_id = hit ? face : -1;
-                    r.range = hit ? range : 0.f; r.energy = dbg_energy; r.n_children = (int)n_child;
-                    P.dbg_casts[(size_t)task * P.dbg_cast_cap_w + warp_casts + i] = r;
-                }
-                next_n += __popc(m0) + __popc(m1);
-                sig_off += __popc(ms0) + __popc(ms1);
+        /* ordered compaction inside the group (reflection before refraction, parents in list order).
+         * The reference also builds waves_new in its last pass and drops it (RadarCPU.cpp:380-389):
+         * nothing traces those waves, so the last pass appends none (n_children is still reported). */
+        const uint32_t act_mask = __ballot_sync(RR_FULL, active);
+        warp_casts += __popc(act_mask);
+        warp_hits += __popc(__ballot_sync(RR_FULL, hit));
+        warp_sigs += __popc(__ballot_sync(RR_FULL, n_sig >= 1)) + __popc(__ballot_sync(RR_FULL, n_sig >= 2));
+        if (!last_pass) {
+            const uint32_t m0 = __ballot_sync(RR_FULL, keep0), m1 = __ballot_sync(RR_FULL, keep1);
+            size_t co = (size_t)g * 64u + __popc(m0 & lt_mask) + __popc(m1 & lt_mask);
+            const float skip = 0.001f;                                     /* RadarCPU.cpp:374-378 */
+            if (keep0) {
+                const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d0, skip));
+                nf[0 * sc + co] = o2.x; nf[1 * sc + co] = o2.y; nf[2 * sc + co] = o2.z;
+                nf[3 * sc + co] = c_d0.x; nf[4 * sc + co] = c_d0.y; nf[5 * sc + co] = c_d0.z;
+                ndp[0 * sc + co] = c_e0; ndp[1 * sc + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
+                nm[co] = c_m0; ni[co] = item;
+                co++;
             }
-            if (lane == 0) {
-                seg[pass] = min(sig_off, scap) - min(seg_start, scap);
-                atomicAdd(&P.item_pass_waves[(size_t)item * RR_MAX_PASSES + pass], n_cur);
-                if (DEBUG) P.dbg_counts[(size_t)task * RR_MAX_PASSES + pass] = n_cur;
+            if (keep1) {
+                const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d1, skip));
+                nf[0 * sc + co] = o2.x; nf[1 * sc + co] = o2.y; nf[2 * sc + co] = o2.z;
+                nf[3 * sc + co] = c_d1.x; nf[4 * sc + co] = c_d1.y; nf[5 * sc + co] = c_d1.z;
+                ndp[0 * sc + co] = c_e1; ndp[1 * sc + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
+                nm[co] = c_m1; ni[co] = item;
             }
-            warp_casts += n_cur;
-            if ((next_n > cap || sig_off > scap) && lane == 0) atomicExch(&P.error_flags[0], 1);
-            n_cur = min(next_n, cap);
-            cur ^= 1;
-            __syncwarp();                                /* children written by other lanes are read next pass */
+            if (lane == 0) {                           /* group count + its 1024-group partial sum (rr_scan_kernel) */
+                const uint32_t c = __popc(m0) + __popc(m1);
+                gcount[g] = c;
+                if (c) atomicAdd(super_next + (g >> 10), c);
+            }
+            if (active) {                              /* the next list's per-item lengths (items are contiguous runs) */
+                const uint32_t peers = __match_any_sync(act_mask, item);
+                const uint32_t c = __popc(m0 & peers) + __popc(m1 & peers);
+                if ((peers & lt_mask) == 0u && c) { atomicAdd(item_count_next + item, c); atomicAdd(item_super_next + (item >> 10), c); }
+            }
         }
-        if (lane == 0) {
-            atomicAdd(&P.counters[0], (unsigned long long)warp_casts);
-            atomicAdd(&P.counters[1], (unsigned long long)warp_hits);
-            atomicAdd(&P.counters[2], (unsigned long long)min(sig_off, scap));
-        }
+    }
+    if (lane == 0 && warp_casts) {
+        atomicAdd(&P.counters[0], (unsigned long long)warp_casts);
+        atomicAdd(&P.counters[1], (unsigned long long)warp_hits);
+        atomicAdd(&P.counters[2], (unsigned long long)warp_sigs);
     }
     if (STATS) {
 #pragma unroll
@@ -469,7 +450,91 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Kernel 2/2: rr_draw_kernel — returns -> range column (RadarCPU.cpp:402-450) -> energy_max, ambient noise,
+ * Kernel 2/3: rr_scan_kernel — between two passes: child counts of the groups of pass `pass - 1` -> exclusive prefix
+ * group_base[] (+ total = list length of `pass`), first_src[] of the new list's groups, and the per-item counts ->
+ * item_start[pass][]. One CTA per 1024 counts; the offset of a CTA is the sum of the 1024-count partial sums the trace
+ * kernel accumulated (super_count / item_super), so there is no chained wait between CTAs. Order-preserving by
+ * construction (prefix sums), so the new list is the reference's.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t rr_block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t nb = __shfl_up_sync(RR_FULL, incl, off); if (lane >= off) incl += nb; }
+    __syncthreads();                                   /* s_warp may still be read from the previous call */
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t wv = (lane < RR_SCAN_BLOCK / 32) ? s_warp[lane] : 0u;
+        uint32_t wi = wv;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t nb = __shfl_up_sync(RR_FULL, wi, off); if (lane >= off) wi += nb; }
+        if (lane < RR_SCAN_BLOCK / 32) s_warp[lane] = wi - wv;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[wid] + incl - v;
+}
+
+__global__ void __launch_bounds__(RR_SCAN_BLOCK) rr_scan_kernel(const RRFrameParams P, const int pass)
+{
+    __shared__ uint32_t s_warp[33];
+    const uint32_t tid = threadIdx.x, b = blockIdx.x;
+    const uint32_t S = (uint32_t)P.n_samples;
+    const uint32_t n_prev = (pass == 1) ? (uint32_t)P.n_items * S : min(P.pass_total[pass - 1], P.wave_cap);
+    const uint32_t n_groups = (n_prev + 31u) >> 5;
+    const uint32_t n_super = (n_groups + RR_SCAN_BLOCK - 1) / RR_SCAN_BLOCK;
+    uint32_t* gb = P.group_base + (size_t)(pass & 1) * (P.group_cap + 1);
+    /* ---- groups: CTA b owns groups [1024 b, 1024 b + 1024); the trace kernel already summed them into super_count[b] */
+    if (b < n_super) {
+        const uint32_t* sc = P.super_count + (size_t)pass * P.super_stride;
+        uint32_t part = 0, before, dummy;
+        for (uint32_t i = tid; i < b; i += RR_SCAN_BLOCK) part += sc[i];
+        rr_block_exclusive_scan(part, s_warp, &before);            /* before = children of all earlier CTAs' groups */
+        const uint32_t g = b * RR_SCAN_BLOCK + tid;
+        const uint32_t c = (g < n_groups) ? gb[g] : 0u;
+        uint32_t tile_total;
+        const uint32_t base = before + rr_block_exclusive_scan(c, s_warp, &tile_total);
+        if (g < n_groups) {
+            gb[g] = base;
+            for (uint32_t go = (base + 31u) >> 5; go * 32u < base + c && go <= P.group_cap; go++) P.first_src[go] = g;
+        }
+        if (b == n_super - 1 && tid == 0) {
+            const uint32_t total = before + tile_total;
+            gb[n_groups] = total;                       /* sentinel: ends the slot walk of the trace kernel */
+            P.pass_total[pass] = total;
+            if (total > P.wave_cap) atomicExch(&P.error_flags[0], 1);
+        }
+        (void)dummy;
+    } else if (b == 0 && tid == 0) {                    /* empty previous list */
+        gb[0] = 0u; P.pass_total[pass] = 0u;
+    }
+    /* ---- items: CTA b owns items [1024 b, 1024 b + 1024) */
+    const uint32_t n_items = (uint32_t)P.n_items;
+    const uint32_t n_isuper = (n_items + RR_SCAN_BLOCK - 1) / RR_SCAN_BLOCK;
+    if (b < n_isuper) {
+        uint32_t* is = P.item_start + (size_t)pass * P.item_stride;
+        const uint32_t* isc = P.item_super + (size_t)pass * P.item_super_stride;
+        uint32_t part = 0, before;
+        for (uint32_t i = tid; i < b; i += RR_SCAN_BLOCK) part += isc[i];
+        rr_block_exclusive_scan(part, s_warp, &before);
+        const uint32_t it = b * RR_SCAN_BLOCK + tid;
+        const uint32_t c = (it < n_items) ? is[it] : 0u;
+        uint32_t tile_total;
+        const uint32_t base = before + rr_block_exclusive_scan(c, s_warp, &tile_total);
+        if (it < n_items) is[it] = base;
+        if (b == n_isuper - 1 && tid == 0) is[n_items] = before + tile_total;
+        uint32_t longest = c;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) longest = max(longest, __shfl_xor_sync(RR_FULL, longest, off));
+        if ((tid & 31u) == 0u) atomicMax(&P.counters[5], (unsigned long long)max(longest, (pass == 1) ? S : 0u));
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernel 3/3: rr_draw_kernel — returns -> range column (RadarCPU.cpp:402-450) -> energy_max, ambient noise,
  * normalise, mono8 (RadarCPU.cpp:453-542). One CTA per (pose, azimuth); the column lives in shared memory.
  *
  * Accumulation is in the reference's order WITHOUT atomics: every bin has exactly one owner thread (its warp by a
@@ -477,7 +542,8 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
  * additions in program order = list order and the float column is bit-identical to the sequential reference loop.
  * Returns cluster in range (a wall = a few hundred adjacent bins), so the partition is ADAPTIVE: a shared-memory
  * histogram of splat load per granule is prefix-summed and cut into 8 ranges of equal load. Every warp replays the
- * (pass, chunk) segments; 32 returns are tested at once (ballot) and only those overlapping its range are applied.
+ * item's returns pass by pass (the wave lists ARE the signal order); 32 waves are tested at once (ballot) and only
+ * the returns overlapping the warp's range are applied.
  * ---------------------------------------------------------------------------------------------- */
 template <bool DEBUG>
 __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P)
@@ -488,6 +554,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     __shared__ float s_red[RR_WARPS];
     __shared__ uint32_t s_load[RR_MAX_GRANULES];
     __shared__ int s_bound[RR_WARPS + 1];
+    __shared__ uint32_t s_begin[RR_MAX_PASSES], s_end[RR_MAX_PASSES];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t item = blockIdx.x;
@@ -495,12 +562,21 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
     const int C = P.n_cells;
     const int n_passes = P.n_passes;
-    const uint32_t n_chunks = (uint32_t)P.n_chunks, scap = P.sig_cap_w;
     for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? (double)P.denoise_weights[i] : 0.0;
     for (int i = tid; i < 256; i += RR_BLOCK) s_perm[i] = c_perlin_perm[i];
     const int n_gran = (C + 31) >> 5;                              /* <= 313 for n_cells <= 10000 */
     for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
     for (int i = tid; i < RR_MAX_GRANULES; i += RR_BLOCK) s_load[i] = 0u;
+    if (tid < n_passes) {                                          /* this item's run of every pass list */
+        const uint32_t S = (uint32_t)P.n_samples;
+        uint32_t b, e, lim;
+        if (tid == 0) { b = item * S; e = b + S; lim = (uint32_t)P.n_items * S; }
+        else {
+            const uint32_t* is = P.item_start + (size_t)tid * P.item_stride;
+            b = is[item]; e = is[item + 1]; lim = min(P.pass_total[tid], P.wave_cap);
+        }
+        s_begin[tid] = min(b, lim); s_end[tid] = min(e, lim);
+    }
     __syncthreads();
 
     const int W = P.denoise_on ? P.denoise_width : 1;
@@ -508,18 +584,18 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
 
     /* ---- 1. splat load per 32-bin granule (any order: integer atomics) */
-    for (uint32_t ch = 0; ch < n_chunks; ch++) {
-        const size_t task = (size_t)item * n_chunks + ch;
-        const uint32_t* seg = P.seg_counts + task * RR_MAX_PASSES;
-        uint32_t n_ret = 0;
-        for (int p2 = 0; p2 < n_passes; p2++) n_ret += seg[p2];
-        const int32_t* pc = P.sig_cell + task * scap;
-        for (uint32_t k = tid; k < n_ret; k += RR_BLOCK) {
-            const int cell = pc[k];
-            if (!(cell < C) || !(cell > -RR_MAX_DENOISE - 1)) continue;
-            const int st = cell - mode;
-            const int g_lo = max(st, lo_bin) >> 5, g_hi = (min(st + W, C) - 1) >> 5;
-            for (int g = g_lo; g <= g_hi; g++) atomicAdd(&s_load[g], 1u);
+    for (int pass = 0; pass < n_passes; pass++) {
+        const int2* pc = P.sig_cell + (size_t)pass * P.wave_cap;
+        for (uint32_t k = s_begin[pass] + tid; k < s_end[pass]; k += RR_BLOCK) {
+            const int2 cc = pc[k];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int cell = q ? cc.y : cc.x;
+                if (!(cell < C) || !(cell > -RR_MAX_DENOISE - 1)) continue;
+                const int st = cell - mode;
+                const int g_lo = max(st, lo_bin) >> 5, g_hi = (min(st + W, C) - 1) >> 5;
+                for (int g = g_lo; g <= g_hi; g++) atomicAdd(&s_load[g], 1u);
+            }
         }
     }
     __syncthreads();
@@ -556,45 +632,42 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
 
     /* ---- 3. ordered accumulation */
     float m = 0.0f;
+    auto splat = [&](const int st, const float sv) {
+        const double svd = (double)sv;
+        const int lo = max(max(st, lo_bin), my_lo), hi = min(min(st + W, C), my_hi);
+        for (int g = lo + ((lane - lo) & 31); g < hi; g += 32) {      /* bin g <-> lane g & 31, always */
+            float v;
+            if (P.denoise_on) {
+                v = (float)((double)s_col[g] + svd * s_weights[g - st]);
+            } else {
+                const float old = s_col[g];
+                v = (old < sv) ? sv : old;                             /* std::max(old, strength), :439 */
+            }
+            s_col[g] = v;
+            if (v > m) m = v;                                          /* running max_val, :428-431 */
+        }
+    };
     if (my_lo < my_hi) {
         for (int pass = 0; pass < n_passes; pass++) {
-            for (uint32_t ch = 0; ch < n_chunks; ch++) {
-                const size_t task = (size_t)item * n_chunks + ch;
-                const uint32_t* seg = P.seg_counts + task * RR_MAX_PASSES;
-                const uint32_t cnt = seg[pass];
-                if (cnt == 0) continue;
-                uint32_t start_off = 0;
-                for (int p2 = 0; p2 < pass; p2++) start_off += seg[p2];
-                const int32_t* pc = P.sig_cell + task * scap + start_off;
-                const float* pst = P.sig_strength + task * scap + start_off;
-                for (uint32_t base = 0; base < cnt; base += 32) {
-                    const bool valid = base + lane < cnt;
-                    const int cell = valid ? pc[base + lane] : 0;
-                    const float str = valid ? pst[base + lane] : 0.f;
-                    /* cell < C (:414); very negative cells (time = -inf/NaN) can not reach a bin */
-                    const int start = cell - mode;
-                    const bool rel = valid && (cell < C) && (cell > -RR_MAX_DENOISE - 1)
-                                     && (max(start, lo_bin) < my_hi) && (min(start + W, C) > my_lo);
-                    uint32_t mask = __ballot_sync(RR_FULL, rel);
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int st = __shfl_sync(RR_FULL, start, j);
-                        const float sv = __shfl_sync(RR_FULL, str, j);
-                        const double svd = (double)sv;
-                        const int lo = max(max(st, lo_bin), my_lo), hi = min(min(st + W, C), my_hi);
-                        for (int g = lo + ((lane - lo) & 31); g < hi; g += 32) {     /* bin g <-> lane g & 31, always */
-                            float v;
-                            if (P.denoise_on) {
-                                v = (float)((double)s_col[g] + svd * s_weights[g - st]);
-                            } else {
-                                const float old = s_col[g];
-                                v = (old < sv) ? sv : old;                 /* std::max(old, strength), :439 */
-                            }
-                            s_col[g] = v;
-                            if (v > m) m = v;                              /* running max_val, :428-431 */
-                        }
-                    }
+            const int2* pc = P.sig_cell + (size_t)pass * P.wave_cap;
+            const float2* pst = P.sig_strength + (size_t)pass * P.wave_cap;
+            const uint32_t e = s_end[pass];
+            for (uint32_t base = s_begin[pass]; base < e; base += 32) {
+                const bool valid = base + lane < e;
+                const int2 cc = valid ? pc[base + lane] : make_int2(INT32_MIN, INT32_MIN);
+                /* cell < C (:414); very negative cells (no return, time = -inf/NaN) can not reach a bin */
+                const int start0 = cc.x - mode, start1 = cc.y - mode;
+                const bool rel0 = (cc.x < C) && (cc.x > -RR_MAX_DENOISE - 1) && (max(start0, lo_bin) < my_hi) && (min(start0 + W, C) > my_lo);
+                const bool rel1 = (cc.y < C) && (cc.y > -RR_MAX_DENOISE - 1) && (max(start1, lo_bin) < my_hi) && (min(start1 + W, C) > my_lo);
+                float2 str = make_float2(0.f, 0.f);
+                if (rel0 || rel1) str = pst[base + lane];
+                uint32_t mask0 = __ballot_sync(RR_FULL, rel0), mask1 = __ballot_sync(RR_FULL, rel1);
+                while (mask0 | mask1) {
+                    const int j = __ffs(mask0 | mask1) - 1;
+                    const uint32_t bit = 1u << j;
+                    if (mask0 & bit) splat(__shfl_sync(RR_FULL, start0, j), __shfl_sync(RR_FULL, str.x, j));
+                    if (mask1 & bit) splat(__shfl_sync(RR_FULL, start1, j), __shfl_sync(RR_FULL, str.y, j));
+                    mask0 &= ~bit; mask1 &= ~bit;
                 }
             }
         }
@@ -649,11 +722,6 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
         if (P.column_major) out[i] = px; else out[(size_t)i * RR_N_ANGLES] = px;
     }
 
-    if (tid == 0) {
-        unsigned long long mw = 0;
-        for (int p2 = 0; p2 < n_passes; p2++) mw = max(mw, (unsigned long long)P.item_pass_waves[(size_t)item * RR_MAX_PASSES + p2]);
-        atomicMax(&P.counters[5], mw);
-    }
 }
 
 /* raw closest-hit probe (rr_cast_rays) */
@@ -674,11 +742,20 @@ __global__ void rr_cast_kernel(const RRNode* nodes, const float4* tris, uint32_t
 }
 
 /* ---- host-side launchers (called from rr_api.cu) ------------------------------------------------*/
-extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int grid, cudaStream_t st, int stats, int debug)
+extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats, int debug)
 {
-    if (debug) rr_trace_kernel<true, true><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P);
-    else if (stats) rr_trace_kernel<true, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P);
-    else rr_trace_kernel<false, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P);
+    if (debug) rr_trace_kernel<true, true><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    else if (stats) rr_trace_kernel<true, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    else rr_trace_kernel<false, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStream_t st)
+{
+    /* one CTA per 1024 groups / 1024 items that the list can hold; CTAs beyond the actual list length exit at once */
+    const uint32_t n_super = (P->group_cap + RR_SCAN_BLOCK - 1) / RR_SCAN_BLOCK, n_isuper = ((uint32_t)P->n_items + RR_SCAN_BLOCK - 1) / RR_SCAN_BLOCK;
+    const uint32_t grid = n_super > n_isuper ? n_super : n_isuper;
+    rr_scan_kernel<<<grid ? grid : 1, RR_SCAN_BLOCK, 0, st>>>(*P, pass);
     return cudaGetLastError();
 }
 

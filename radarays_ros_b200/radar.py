@@ -102,6 +102,10 @@ class RadarB200:
     def setMaxWavesPerAzimuth(self, n):
         capi.check(self._ctx, self._lib.rr_set_max_waves_per_azimuth(self._ctx, n))
 
+    def setLanes(self, n):
+        """1 = strictly serial kernel launches (per-kernel timing); default 2 overlaps sub-batches of a call."""
+        capi.check(self._ctx, self._lib.rr_set_lanes(self._ctx, n))
+
     # ---- the hot path --------------------------------------------------------------------------------------------
     @staticmethod
     def _poses(poses):
@@ -116,9 +120,11 @@ class RadarB200:
             arr[i] = p if isinstance(p, Pose) else Pose.from_xyz_yaw(*p)
         return arr
 
-    def simulate(self, Tsm, frame_id=None, return_stats=False):
+    def simulate(self, Tsm, frame_id=None, return_stats=False, out=None):
         """One frame (Pose), a batch (sequence of Pose) or, with cfg.include_motion, 400 poses per frame.
-        Returns uint8 (n_cells, 400) / (n, n_cells, 400); None when Tsm is None (RadarCPU.cpp:129-133)."""
+        Returns uint8 (n_cells, 400) / (n, n_cells, 400); None when Tsm is None (RadarCPU.cpp:129-133).
+        `out`: optional caller-owned uint8 array (n, n_cells, 400) to fill instead of a fresh one; when it is
+        page-locked (e.g. a torch pin_memory tensor viewed as numpy) the images are copied straight into it."""
         if Tsm is None:
             if not self.has_last:
                 return None
@@ -130,7 +136,13 @@ class RadarB200:
         if frame_id is None:
             frame_id = self.frame_counter
         self.frame_counter = frame_id + n
-        out = np.empty((n, self.m_cfg.n_cells, N_ANGLES), np.uint8)
+        shape = (n, self.m_cfg.n_cells, N_ANGLES)
+        if out is None:
+            out = np.empty(shape, np.uint8)
+        elif out.dtype != np.uint8 or out.size != n * shape[1] * shape[2] or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous uint8 array of shape %s" % (shape,))
+        else:
+            out = out.reshape(shape)
         st = Stats()
         fn = self._lib.rr_simulate_motion if motion else self._lib.rr_simulate
         capi.check(self._ctx, fn(self._ctx, arr, n, frame_id, _ptr(out), C.byref(st)))
