@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="debug: ~60k-triangle mesh instead of urban-5M")
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames in the bounded cpu_baseline sample")
+    ap.add_argument("--lanes", type=int, default=2, help="internal streams per call (rr_set_lanes); 1 = serial launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -205,6 +206,7 @@ def main():
     scene = make_scene(args.small)
     t_scene = time.time() - t0
     radar = RadarB200(scene, cfg, device=local_rank, beam_seed=beam_seed, noise_seed=noise_seed)
+    radar.setLanes(args.lanes)
     dirs = radar.getBeamSamples()
     poses = rank_poses(scene, rank, args.small)
     poses_np = np.frombuffer(poses, dtype=np.float32).reshape(POSES_PER_STEP, 7).copy()
@@ -265,7 +267,7 @@ def main():
             step((W + s) * POSES_PER_STEP)
     torch.cuda.synchronize()
     trace_ms_sum, draw_ms_sum, n_pairs = radar.kernel_times()     # events around the kernels, on the launch stream
-    radar.setLanes(2)
+    radar.setLanes(args.lanes)
 
     # end-to-end through the public host-buffer API (pinned H2D poses, D2H images inside the timed region)
     # caller-owned page-locked result buffer, as a ROS node would keep for its sensor_msgs::Image payloads

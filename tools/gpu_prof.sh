@@ -1,4 +1,8 @@
 cd /root/repo
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:"rr_trace_kernel|rr_scan_kernel|rr_draw_kernel" --launch-skip 104 -c 1 -o gpurun_out/prof_trace_v6_p1 -f python bench.py --steps 2 --warmup 1 --cpu-frames 0 > gpurun_out/prof_v6.log 2>&1
-tail -3 gpurun_out/prof_v6.log | cut -c1-300
+for v in r32 r8w10; do
+RADARAYS_B200_LIB=$PWD/variants/lib_$v.so ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,l1tex__t_sector_hit_rate.pct,lts__t_sector_hit_rate.pct \
+    --clock-control none -k regex:"rr_walk_kernel|rr_shade_kernel|rr_scan_kernel|rr_draw_kernel" --launch-skip 153 -c 9 --csv \
+    --log-file gpurun_out/v7_${v}_launches.csv python bench.py --steps 2 --warmup 1 --cpu-frames 0 --lanes 1 > gpurun_out/v7_launches.log 2>&1
+python tools/summarize_launches.py gpurun_out/v7_${v}_launches.csv
+done
