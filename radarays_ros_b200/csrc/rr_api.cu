@@ -45,6 +45,7 @@ struct rr_ctx {
     bool have_params = false;
     rr_config cfg; rr_model model;
     float* d_weights = nullptr; int denoise_width = 0, denoise_mode = 0;
+    float* d_noise_decay = nullptr; size_t d_noise_decay_cap = 0;   /* exp(-loss * range(i)) per cell, RadarCPU.cpp:521 */
     /* beam samples */
     std::vector<float> beam; bool beam_user = false; bool resample = true; uint64_t beam_seed = 0;
     float* d_beam = nullptr; size_t d_beam_n = 0;
@@ -329,7 +330,7 @@ void rr_destroy(rr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials);
-    cudaFree(ctx->d_weights); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
+    cudaFree(ctx->d_weights); cudaFree(ctx->d_noise_decay); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
     free_lane_scratch(ctx);
     for (int l = 0; l < rr_ctx::kLanes; l++) {
         cudaFree(ctx->lanes[l].d_ctrl);
@@ -447,6 +448,20 @@ int rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg)
     std::copy(w.begin(), w.end(), wpad.begin());
     CK(cudaMemcpy(ctx->d_weights, wpad.data(), RR_MAX_DENOISE * sizeof(float), cudaMemcpyHostToDevice));
     ctx->denoise_width = (int)w.size(); ctx->denoise_mode = mode;
+    /* range attenuation of the ambient noise floor, exp(-loss * x_i) with x_i the centre of cell i (RadarCPU.cpp:517-521):
+     * depends on the parameters only, so it is tabulated here once with the same rr_detmath.h routine the kernels use
+     * (bit-identical on host and device) instead of being re-evaluated for every cell of every column. */
+    {
+        const int C = std::max(cfg->n_cells, 1);
+        std::vector<float> decay((size_t)C);
+        const float e_loss = (float)cfg->ambient_noise_energy_loss;
+        for (int i = 0; i < C; i++) {
+            const float x = (float)(((double)(float)i + 0.5) * cfg->resolution);
+            decay[i] = rr_expf(-e_loss * x);
+        }
+        CK(regrow(&ctx->d_noise_decay, &ctx->d_noise_decay_cap, (size_t)C));
+        CK(cudaMemcpy(ctx->d_noise_decay, decay.data(), (size_t)C * sizeof(float), cudaMemcpyHostToDevice));
+    }
     ctx->have_params = true;
     return RR_OK;
 }
@@ -584,7 +599,7 @@ static void fill_params(rr_ctx* ctx, RRFrameParams& P)
     P.n_cells = c.n_cells; P.scroll_image = c.scroll_image; P.resolution = c.resolution;
     P.energy_max_f = (float)c.energy_max; P.signal_max = c.signal_max;
     P.denoise_on = c.signal_denoising > 0 ? 1 : 0; P.denoise_width = ctx->denoise_width; P.denoise_mode = ctx->denoise_mode;
-    P.denoise_weights = ctx->d_weights;
+    P.denoise_weights = ctx->d_weights; P.noise_decay = ctx->d_noise_decay;
     P.ambient_noise = c.ambient_noise;
     P.noise_at_signal_0 = c.ambient_noise_at_signal_0; P.noise_at_signal_1 = c.ambient_noise_at_signal_1;
     P.noise_energy_max = c.ambient_noise_energy_max; P.noise_energy_min = c.ambient_noise_energy_min;

@@ -40,7 +40,9 @@ struct RRBuildNode {
 
 /* ---- kernel parameter block ---------------------------------------------------------------------*/
 #define RR_MAX_DENOISE 256
-#define RR_BLOCK 256
+#ifndef RR_BLOCK
+#define RR_BLOCK 128              /* rr_draw_kernel CTA: RR_WARPS warps share one (pose, azimuth) column */
+#endif
 #define RR_WARPS (RR_BLOCK / 32)
 #define RR_TRACE_BLOCK 128       /* trace kernel: 4 independent warps per CTA */
 #define RR_GROUP 32              /* waves per trace group (= one warp round) */
@@ -79,6 +81,7 @@ struct RRFrameParams {
     double signal_max;
     int32_t denoise_on, denoise_width, denoise_mode;
     const float* denoise_weights;
+    const float* noise_decay;      /* [n_cells] exp(-(float)noise_energy_loss * centre range of cell i), host-tabulated */
     int32_t ambient_noise;
     double noise_at_signal_0, noise_at_signal_1, noise_energy_max, noise_energy_min, noise_energy_loss;
     int32_t record_multi_reflection, record_multi_path;

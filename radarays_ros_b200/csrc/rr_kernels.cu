@@ -688,7 +688,6 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     const float noise_at_1 = (float)((double)signal_amp * P.noise_at_signal_1);
     const float ne_max = (float)((double)max_val * P.noise_energy_max);
     const float ne_min = (float)((double)max_val * P.noise_energy_min);
-    const float e_loss = (float)P.noise_energy_loss;
     const double random_begin = (P.ambient_noise == 2)
         ? (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 0u) * 1000.0 : 0.0;
     const float out_scale = (float)(P.signal_max / (double)max_val);
@@ -711,8 +710,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
             const float sn4 = (float)rr_pow4(sn);
             const float amp = (float)((double)(sn4 * noise_at_0) + (1.0 - (double)sn4) * (double)noise_at_1);
             float y = (float)((double)amp * p);
-            const float x = (float)(((double)(float)i + 0.5) * P.resolution);
-            y = y + (ne_max - ne_min) * rr_expf(-e_loss * x) + ne_min;
+            y = y + (ne_max - ne_min) * __ldg(P.noise_decay + i) + ne_min;   /* exp(-loss * x_i), :517-521 */
             y = fabsf(y);
             v = v + y;
         }
