@@ -1,0 +1,92 @@
+"""GPU edge cases of the launch-wide wavefront (rr_internal.h): empty lists, ragged list lengths, list overflow,
+sub-batch / lane splitting. All comparisons are bit-exact against the CPU oracle or against the single-pose result."""
+import numpy as np
+import pytest
+
+from radarays_ros_b200 import RadarModelConfig, MULRAN_DYNCFG, Pose, scenes
+from radarays_ros_b200.capi import RadaRaysError
+from radarays_ros_b200.radar import RadarB200
+from radarays_ros_b200.scenes import Scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _one_triangle_scene(z):
+    """A single small triangle far below the sensor plane: every beam ray misses."""
+    v = np.array([[0, 0, z], [1, 0, z], [0, 1, z]], np.float32)
+    t = np.array([[0, 1, 2]], np.uint32)
+    return Scene("one-triangle", v, t, np.zeros(1, np.uint32), [(0.3, 1.0, 0.0, 1.0), (0.0, 1.0, 0.0, 3000.0)], [1],
+                 0, [(0.0, 0.0, 0.0, 0.0)])
+
+
+@pytest.mark.parametrize("noise", [0, 2])
+def test_all_rays_miss(oracle_mod, noise):
+    """pass 0 produces no child: the lists of passes 1.. are empty (pass_total = 0) and every column is noise only
+    (quirk 14: max_val = 0 -> 0/0 -> NaN -> 0)."""
+    sc = _one_triangle_scene(-500.0)
+    cfg = RadarModelConfig(n_reflections=3, n_samples=40, ambient_noise=noise, include_motion=0, n_cells=512)
+    radar = RadarB200(sc, cfg, beam_seed=5, noise_seed=6)
+    img, st = radar.simulate(sc.pose_array()[0], frame_id=1, return_stats=True)
+    assert st.n_casts == 400 * 40 and st.n_hits == 0 and st.n_signals == 0
+    o = oracle_mod.OracleScene(sc).simulate(cfg, radar.getBeamSamples(), sc.pose_array()[:1], noise_seed=6, frame_id=1)
+    assert np.array_equal(img, o["image"])
+
+
+def test_ragged_lists_and_lane_split(oracle_mod):
+    """n_samples = 37 (not a multiple of the 32-wave group), dielectric splits (warehouse glass) so that azimuth runs
+    straddle groups; 5 poses so that the sub-batches of the two lanes are uneven. One lane == two lanes == per pose."""
+    sc = scenes.warehouse_small()
+    cfg = RadarModelConfig(**dict(MULRAN_DYNCFG, n_samples=37, n_reflections=4, n_cells=900, resolution=0.03))
+    radar = RadarB200(sc, cfg, beam_seed=3, noise_seed=4)
+    radar.setMaxWavesPerAzimuth(37 * 16)
+    poses = sc.pose_array(5)
+    two = radar.simulate(poses, frame_id=50).copy()
+    radar.setLanes(1)
+    one = radar.simulate(poses, frame_id=50).copy()
+    radar.setLanes(2)
+    assert np.array_equal(one, two), "result depends on the number of lanes"
+    osc = oracle_mod.OracleScene(sc)
+    dirs = radar.getBeamSamples()
+    for i in (0, 4):
+        o = osc.simulate(cfg, dirs, poses[i:i + 1], noise_seed=4, frame_id=50 + i)
+        assert np.array_equal(two[i], o["image"]), "pose %d of the batch differs from the oracle" % i
+        single = radar.simulate(poses[i], frame_id=50 + i)
+        assert np.array_equal(single, two[i])
+
+
+def test_wave_list_overflow_is_reported():
+    """A list longer than max_waves_per_azimuth * azimuths must come back as RR_ERR_WAVE_OVERFLOW (-5), not as a
+    silently truncated image (the reference's std::vector just grows, RadarCPU.cpp:380-389)."""
+    sc = scenes.warehouse_small()
+    cfg = RadarModelConfig(**dict(MULRAN_DYNCFG, n_samples=64, n_reflections=5, n_cells=900, resolution=0.03))
+    radar = RadarB200(sc, cfg, beam_seed=3, noise_seed=4)
+    _, st = radar.simulate(sc.pose_array()[0], frame_id=0, return_stats=True)
+    assert st.overflow == 0
+    assert st.max_waves >= 64
+    # capacity below what pass 0 itself needs is clamped to n_samples; make later passes overflow instead
+    if st.n_casts > 400 * 64 * 5:        # the scene splits waves somewhere: total casts exceed samples * passes
+        radar.setMaxWavesPerAzimuth(64)
+        with pytest.raises(RadaRaysError) as ei:
+            radar.simulate(sc.pose_array()[0], frame_id=0)
+        assert ei.value.code == -5
+        radar.setMaxWavesPerAzimuth(64 * 16)
+        img = radar.simulate(sc.pose_array()[0], frame_id=0)
+        assert img.max() > 0
+
+
+def test_caller_buffer_and_pinned_output(oracle_mod):
+    """rr_simulate writes into a caller-owned buffer; a page-locked one is filled by direct device->host copies."""
+    import torch
+    sc = scenes.urban_small()
+    cfg = RadarModelConfig(**dict(MULRAN_DYNCFG, n_samples=16, n_reflections=2, n_cells=768))
+    radar = RadarB200(sc, cfg, beam_seed=1, noise_seed=2)
+    poses = sc.pose_array(6)
+    ref = radar.simulate(poses, frame_id=10).copy()
+    pinned = torch.zeros((6, 768, 400), dtype=torch.uint8).pin_memory()
+    out = radar.simulate(poses, frame_id=10, out=pinned.numpy())
+    assert np.array_equal(out, ref) and np.array_equal(pinned.numpy(), ref)
+    pageable = np.zeros((6, 768, 400), np.uint8)
+    radar.simulate(poses, frame_id=10, out=pageable)
+    assert np.array_equal(pageable, ref)
+    with pytest.raises(ValueError):
+        radar.simulate(poses, frame_id=10, out=np.zeros((5, 768, 400), np.uint8))
