@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 1
+#define RR_ABI_VERSION 2
 #define RR_N_ANGLES 400            /* Radar.cpp:27-29: theta.size = 400, theta.inc = -(2 pi)/400 */
 
 typedef enum {
@@ -116,6 +116,13 @@ typedef struct {
     int32_t  overflow;         /* 1 if any azimuth hit RR_ERR_WAVE_OVERFLOW */
 } rr_stats;
 
+/* msg/RadarParams.msg:1-2 (materials + model) = the goal of GenRadarImage.action and the reply of GetRadarParams.srv */
+typedef struct {
+    const rr_material* materials;  /* msg/RadarMaterials.msg: data[] */
+    uint32_t           n_materials;
+    rr_model           model;
+} rr_radar_params;
+
 typedef struct rr_ctx rr_ctx;
 
 int         rr_abi_version(void);
@@ -191,6 +198,23 @@ int         rr_get_stats(rr_ctx* ctx, rr_stats* stats);       /* counters of the
  * remembered). Synchronises the device. The reference's counterpart is its stdout stopwatch (RadarCPU.cpp:550-553). */
 int         rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_t* n_launch_pairs);
 int         rr_set_max_waves_per_azimuth(rr_ctx* ctx, uint32_t max_waves);
+/* replaces: the GetRadarParams service (srv/GetRadarParams.srv:1-2, Radar::getParams Radar.hpp:51-54; called by
+ * scripts/radaray_opti.py:135-147). materials_out nullable (size query through n_materials). */
+int         rr_get_radar_params(rr_ctx* ctx, rr_material* materials_out, size_t capacity, size_t* n_materials,
+                                rr_model* model_out);
+/* replaces: the GenRadarImage action (action/GenRadarImage.action:1-6: goal RadarParams -> result polar_image; client
+ * scripts/radaray_opti.py:164-205; the server is missing upstream, radar_simulator.cpp:220-224), BATCHED: goal g is
+ * rendered with ITS materials, beam_width (own beam bundle, unless caller-supplied samples are installed) and
+ * n_reflections from pose Tsm[g] (n_poses == n_goals) or Tsm[0] (n_poses == 1), all goals in one launch sequence.
+ * The context's own RadarParams are not changed (Radar::setParams semantics are rr_set_materials/rr_set_params).
+ * Every goal must keep the context's n_samples and material count. frame_id0 + g keys goal g's noise stream.
+ * out_polar (nullable): n_goals x n_cells x 400 mono8. real_polar (nullable, n_real = 1 or n_goals recorded images
+ * of the same shape): sum_sq_err[g] = sum over pixels of (sim_g - real)^2, computed on the device, i.e. the optimiser's
+ * objective -PSNR = -10 log10(255^2 n_pixels / sum_sq_err[g]) (scripts/radaray_opti.py:198) without moving images. */
+int         rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goals,
+                                const rr_pose* Tsm, size_t n_poses, uint64_t frame_id0,
+                                uint8_t* out_polar, const uint8_t* real_polar, size_t n_real,
+                                double* sum_sq_err, rr_stats* stats /* nullable */);
 /* Concurrency inside one call: the poses of a call are cut into sub-batches that alternate between `n_lanes` internal
  * streams (default 2, each with its own wave lists), so one sub-batch's pass tails, draw kernel and device->host copy
  * overlap the other's traversal. 1 = strictly serial launches, which is what rr_kernel_times needs to time a kernel

@@ -14,6 +14,8 @@
 #include "rr_internal.h"
 
 extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats, int debug);
+extern "C" cudaError_t rr_launch_score(const uint8_t* sim, const uint8_t* real, size_t img_bytes, size_t real_stride,
+                                       size_t n_goals, unsigned long long* ssd, cudaStream_t st);
 extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStream_t st);
 extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
@@ -41,6 +43,13 @@ struct rr_ctx {
     bool have_materials = false;
     float4* d_materials = nullptr; int32_t* d_object_materials = nullptr;
     int n_materials = 0, n_objects = 0, air = 0;
+    std::vector<rr_material> materials_host;      /* for rr_get_radar_params (GetRadarParams.srv) */
+    /* rr_gen_radar_images staging */
+    float4* d_goal_mat = nullptr; size_t d_goal_mat_cap = 0;
+    float* d_goal_beam = nullptr; size_t d_goal_beam_cap = 0;
+    int32_t* d_goal_passes = nullptr; size_t d_goal_passes_cap = 0;
+    uint8_t* d_real = nullptr; size_t d_real_cap = 0;
+    unsigned long long* d_ssd = nullptr; size_t d_ssd_cap = 0;
     /* params */
     bool have_params = false;
     rr_config cfg; rr_model model;
@@ -330,6 +339,7 @@ void rr_destroy(rr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials);
+    cudaFree(ctx->d_goal_mat); cudaFree(ctx->d_goal_beam); cudaFree(ctx->d_goal_passes); cudaFree(ctx->d_real); cudaFree(ctx->d_ssd);
     cudaFree(ctx->d_weights); cudaFree(ctx->d_noise_decay); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
     free_lane_scratch(ctx);
     for (int l = 0; l < rr_ctx::kLanes; l++) {
@@ -410,6 +420,7 @@ int rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materia
     CK(cudaMemcpy(ctx->d_materials, m.data(), n_materials * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_object_materials, object_materials, n_objects * sizeof(int32_t), cudaMemcpyHostToDevice));
     ctx->n_materials = (int)n_materials; ctx->n_objects = (int)n_objects; ctx->air = material_id_air;
+    ctx->materials_host.assign(materials, materials + n_materials);
     ctx->have_materials = true;
     return RR_OK;
 }
@@ -639,6 +650,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
     const rr_pose* poses0 = P.poses;
     uint8_t* out0 = P.out;
     const uint64_t frame0 = P.frame_id0;
+    const float4* mat0 = P.materials; const float* beam0 = P.beam_dirs; const int32_t* passes0 = P.pose_passes;
     const size_t out_stride = P.column_major ? (size_t)P.az_count * P.n_cells : (size_t)P.n_cells * RR_N_ANGLES;
     const int Pn = P.n_passes;
     const int n_sub = (n_total + poses_per_launch - 1) / poses_per_launch;
@@ -661,6 +673,9 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         P.poses = poses0 + (size_t)first * (P.pose_per_azimuth ? RR_N_ANGLES : 1);
         P.out = out0 + (size_t)first * out_stride;
         P.frame_id0 = frame0 + (uint64_t)first;
+        P.materials = mat0 + (size_t)first * P.material_stride;
+        P.beam_dirs = beam0 + (size_t)first * P.beam_stride;
+        P.pose_passes = passes0 ? passes0 + first : nullptr;
         const uint32_t items = (uint32_t)n * (uint32_t)P.az_count;
         P.n_items = (int32_t)items;
         P.wave_cap = (uint32_t)((((size_t)items * ctx->waves_per_item) + 31) & ~(size_t)31);
@@ -698,6 +713,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         CK(cudaStreamWaitEvent(st, ctx->lanes[l].done, 0));
     }
     P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0;
+    P.materials = mat0; P.beam_dirs = beam0; P.pose_passes = passes0;
     return RR_OK;
 }
 
@@ -816,6 +832,128 @@ int rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_
     if (n_launch_pairs) *n_launch_pairs = ctx->tev_count;
     ctx->tev_count = 0;
     return RR_OK;
+}
+
+/* GetRadarParams.srv (srv/GetRadarParams.srv:1-2): the RadarParams the next frame would be rendered with */
+int rr_get_radar_params(rr_ctx* ctx, rr_material* materials_out, size_t capacity, size_t* n_materials, rr_model* model_out)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_materials || !ctx->have_params) return fail(ctx, RR_ERR_NOT_READY, "rr_get_radar_params: materials / params not set");
+    if (n_materials) *n_materials = ctx->materials_host.size();
+    if (materials_out) {
+        if (capacity < ctx->materials_host.size()) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_get_radar_params: capacity %zu < %zu materials", capacity, ctx->materials_host.size());
+        std::copy(ctx->materials_host.begin(), ctx->materials_host.end(), materials_out);
+    }
+    if (model_out) *model_out = ctx->model;
+    return RR_OK;
+}
+
+/* GenRadarImage.action (action/GenRadarImage.action:1-6), batched: goal g = RadarParams -> polar image g, rendered from
+ * Tsm[g] (or Tsm[0]). Every goal keeps its own material table, beam bundle (beam_width) and pass count in one launch. */
+int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goals, const rr_pose* Tsm, size_t n_poses,
+                        uint64_t frame_id0, uint8_t* out_polar, const uint8_t* real_polar, size_t n_real,
+                        double* sum_sq_err, rr_stats* stats)
+{
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!goals || !n_goals || !Tsm) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_gen_radar_images: NULL goals / poses");
+    if (n_poses != 1 && n_poses != n_goals) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_gen_radar_images: n_poses must be 1 or n_goals");
+    if ((real_polar != nullptr) != (sum_sq_err != nullptr) || (real_polar && n_real != 1 && n_real != n_goals))
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_gen_radar_images: real_polar (1 or n_goals images) and sum_sq_err go together");
+    if (!out_polar && !real_polar) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_gen_radar_images: nothing to return (out_polar and real_polar NULL)");
+    const size_t nm = (size_t)ctx->n_materials, S = ctx->model.n_samples;
+    uint32_t max_passes = 0;
+    for (size_t g = 0; g < n_goals; g++) {
+        if (!goals[g].materials || goals[g].n_materials != nm)
+            return fail(ctx, RR_ERR_OUT_OF_RANGE, "goal %zu: %u materials, the scene's object table indexes %zu", g, goals[g].n_materials, nm);
+        if (goals[g].model.n_samples != S)
+            return fail(ctx, RR_ERR_INVALID_ARGUMENT, "goal %zu: n_samples %u differs from the context's %zu (one launch shares the list shape)", g, goals[g].model.n_samples, S);
+        if (goals[g].model.n_reflections < 1 || goals[g].model.n_reflections > RR_MAX_PASSES)
+            return fail(ctx, RR_ERR_INVALID_ARGUMENT, "goal %zu: n_reflections %u outside [1,%d]", g, goals[g].model.n_reflections, RR_MAX_PASSES);
+        max_passes = std::max(max_passes, goals[g].model.n_reflections);
+    }
+    /* per-goal tables */
+    std::vector<float4> mats(n_goals * nm);
+    std::vector<int32_t> passes(n_goals);
+    std::vector<float> beams;
+    const bool per_goal_beam = !ctx->beam_user;           /* caller-supplied m_waves_start overrides beam_width */
+    if (per_goal_beam) beams.resize(n_goals * S * 3);
+    std::vector<float> one;
+    for (size_t g = 0; g < n_goals; g++) {
+        for (size_t i = 0; i < nm; i++) {
+            const rr_material& m = goals[g].materials[i];
+            mats[g * nm + i] = make_float4(m.velocity, m.ambient, m.diffuse, m.specular);
+        }
+        passes[g] = (int32_t)goals[g].model.n_reflections;
+        if (per_goal_beam) {
+            if (g > 0 && goals[g].model.beam_width == goals[g - 1].model.beam_width) {
+                std::copy(beams.begin() + (g - 1) * S * 3, beams.begin() + g * S * 3, beams.begin() + g * S * 3);
+            } else {
+                draw_beam_samples(goals[g].model.beam_width, (int)S, ctx->cfg.beam_sample_dist,
+                                  (float)ctx->cfg.beam_sample_dist_normal_p_in_cone, ctx->beam_seed, one);
+                std::copy(one.begin(), one.end(), beams.begin() + g * S * 3);
+            }
+        }
+    }
+    const rr_model saved_model = ctx->model;
+    ctx->model.n_reflections = max_passes;                 /* list capacity and pass loop of this call */
+    struct Restore { rr_ctx* c; rr_model m; ~Restore() { c->model = m; } } restore{ctx, saved_model};
+    const int min_split = (int)std::min<size_t>(n_goals, 4);
+    if ((rc = ensure_scratch(ctx, ((n_goals + min_split - 1) / min_split) * RR_N_ANGLES))) return rc;
+    const size_t img = (size_t)ctx->cfg.n_cells * RR_N_ANGLES;
+    CK(regrow(&ctx->d_goal_mat, &ctx->d_goal_mat_cap, mats.size()));
+    CK(regrow(&ctx->d_goal_passes, &ctx->d_goal_passes_cap, n_goals));
+    if (per_goal_beam) CK(regrow(&ctx->d_goal_beam, &ctx->d_goal_beam_cap, beams.size()));
+    CK(regrow(&ctx->d_poses, &ctx->d_poses_cap, n_goals));
+    CK(regrow(&ctx->d_out, &ctx->d_out_cap, n_goals * img));
+    CK(regrow(&ctx->h_poses, &ctx->h_poses_cap, n_goals, true));
+    for (size_t g = 0; g < n_goals; g++) ctx->h_poses[g] = Tsm[n_poses == 1 ? 0 : g];
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_poses, ctx->h_poses, n_goals * sizeof(rr_pose), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_goal_mat, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_goal_passes, passes.data(), n_goals * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (per_goal_beam) CK(cudaMemcpyAsync(ctx->d_goal_beam, beams.data(), beams.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (real_polar) {
+        CK(regrow(&ctx->d_real, &ctx->d_real_cap, n_real * img));
+        CK(regrow(&ctx->d_ssd, &ctx->d_ssd_cap, n_goals));
+        CK(cudaMemcpyAsync(ctx->d_real, real_polar, n_real * img, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->d_ssd, 0, n_goals * sizeof(unsigned long long), st));
+    }
+    CK(cudaStreamSynchronize(st));                         /* the pageable host vectors above go out of use here */
+    RRFrameParams P;
+    fill_params(ctx, P);
+    P.poses = ctx->d_poses; P.n_poses = (int)n_goals; P.pose_per_azimuth = 0;
+    P.az_begin = 0; P.az_count = RR_N_ANGLES; P.frame_id0 = frame_id0;
+    P.out = ctx->d_out; P.column_major = 0;
+    P.materials = ctx->d_goal_mat; P.material_stride = (uint32_t)nm;
+    if (per_goal_beam) { P.beam_dirs = ctx->d_goal_beam; P.beam_stride = (uint32_t)(3 * S); }
+    P.pose_passes = ctx->d_goal_passes;
+    RRCopyOut copy;
+    const bool direct = out_polar && host_ptr_is_pinned(out_polar);
+    if (out_polar) {
+        if (!direct) CK(regrow(&ctx->h_out, &ctx->h_out_cap, n_goals * img, true));
+        copy.h_dst = direct ? out_polar : ctx->h_out;
+    }
+    CK(cudaEventRecord(ctx->ev0, st));
+    if ((rc = enqueue(ctx, P, st, 0, 0, min_split, out_polar ? &copy : nullptr))) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    std::vector<unsigned long long> ssd(real_polar ? n_goals : 0);
+    if (real_polar) {
+        CK(rr_launch_score(ctx->d_out, ctx->d_real, img, n_real == 1 ? 0 : img, n_goals, ctx->d_ssd, st));
+        ctx->launches++;
+        CK(cudaMemcpyAsync(ssd.data(), ctx->d_ssd, n_goals * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    }
+    if (out_polar) {
+        for (int k = 0; k < copy.n_sub; k++) {
+            CK(cudaEventSynchronize(ctx->sub_ev[k]));
+            if (!direct) memcpy(out_polar + (size_t)copy.ranges[k].first * img, ctx->h_out + (size_t)copy.ranges[k].first * img, (size_t)copy.ranges[k].second * img);
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    for (size_t g = 0; g < ssd.size(); g++) sum_sq_err[g] = (double)ssd[g];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    return collect(ctx, stats, ms);
 }
 
 int rr_set_lanes(rr_ctx* ctx, int32_t n_lanes)

@@ -64,11 +64,14 @@ struct RRFrameParams {
     const float4* tris;            /* 3 float4 per triangle, leaf order */
     uint32_t root_ref;
     float grid_origin[3], grid_scale[3];
-    const float4* materials;       /* (velocity, ambient, diffuse, specular) */
+    const float4* materials;       /* (velocity, ambient, diffuse, specular); pose p reads materials[p * material_stride + id] */
+    uint32_t material_stride;      /* 0 = one table for all poses; n_materials = one table per goal (rr_gen_radar_images) */
     const int32_t* object_materials;
     int32_t n_materials, n_objects, material_id_air;
     /* beam + poses */
-    const float* beam_dirs;        /* n_samples x 3 */
+    const float* beam_dirs;        /* n_samples x 3; pose p reads beam_dirs + p * beam_stride */
+    uint32_t beam_stride;          /* 0 = one bundle for all poses; 3 * n_samples = one bundle per goal */
+    const int32_t* pose_passes;    /* nullable: passes of pose p (<= n_passes) when goals differ in n_reflections */
     const float4* tas_quat;        /* 400 azimuth rotations Tas.R (x,y,z,w), host-computed */
     const rr_pose* poses;          /* n_poses (or n_poses*400 when pose_per_azimuth) */
     int32_t n_samples, n_passes, n_poses, pose_per_azimuth;

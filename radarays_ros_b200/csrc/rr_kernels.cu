@@ -12,6 +12,7 @@
  * The arithmetic is written independently of oracle/rr_oracle.cpp; only the elementary primitives of
  * rr_detmath.h are shared. Compile with --fmad=false: every fused multiply-add below is explicit.
  */
+#include <algorithm>
 #include "rr_internal.h"
 
 #define RR_FULL 0xffffffffu
@@ -246,7 +247,8 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                 item = j / S;
                 const uint32_t smp = j - item * S;
                 w.o = rr_v3(0.f, 0.f, 0.f);
-                w.d = rr_v3(P.beam_dirs[3 * smp], P.beam_dirs[3 * smp + 1], P.beam_dirs[3 * smp + 2]);
+                const float* bd = P.beam_dirs + (size_t)item / (uint32_t)P.az_count * P.beam_stride;   /* per-goal bundles: rr_gen_radar_images */
+                w.d = rr_v3(bd[3 * smp], bd[3 * smp + 1], bd[3 * smp + 2]);
                 w.energy = 1.0; w.time = 0.0; w.mat = 0u;
             } else {                                      /* list position j -> slot (rr_internal.h) */
                 uint32_t gg = P.first_src[g];
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                     /* medium on the far side (RadarCPU.cpp:266-280) */
                     const uint32_t air = (uint32_t)P.material_id_air;
                     const uint32_t mat_t = (w.mat == air) ? (uint32_t)P.object_materials[obj] : air;
-                    const float4 mt = P.materials[mat_t];
+                    const float4 mt = P.materials[(size_t)pose_i * P.material_stride + mat_t];
                     const float v_t = (w.mat != mat_t) ? mt.x : (float)wave_v;
 
                     /* Snell/Fresnel (radar_algorithms.h:55-139): n1 := v2, n2 := v1 */
@@ -401,6 +403,7 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
         warp_hits += __popc(__ballot_sync(RR_FULL, hit));
         warp_sigs += __popc(__ballot_sync(RR_FULL, n_sig >= 1)) + __popc(__ballot_sync(RR_FULL, n_sig >= 2));
         if (!last_pass) {
+            if (P.pose_passes && active && pass + 1 >= P.pose_passes[item / (uint32_t)P.az_count]) { keep0 = false; keep1 = false; }   /* this goal's last pass */
             const uint32_t m0 = __ballot_sync(RR_FULL, keep0), m1 = __ballot_sync(RR_FULL, keep1);
             size_t co = (size_t)g * 64u + __popc(m0 & lt_mask) + __popc(m1 & lt_mask);
             const float skip = 0.001f;                                     /* RadarCPU.cpp:374-378 */
@@ -720,6 +723,49 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
         if (P.column_major) out[i] = px; else out[(size_t)i * RR_N_ANGLES] = px;
     }
 
+}
+
+/* Sum of squared pixel differences of every rendered goal image against a recorded ("real") polar image: the data
+ * term of the material optimiser's objective, -PSNR (scripts/radaray_opti.py:198, skimage peak_signal_noise_ratio =
+ * 10 log10(255^2 / mean((a-b)^2))). Exact integer arithmetic; grid = (chunks, goals). */
+__global__ void __launch_bounds__(256) rr_score_kernel(const uint8_t* __restrict__ sim, const uint8_t* __restrict__ real,
+                                                       size_t img_bytes, size_t real_stride, unsigned long long* ssd)
+{
+    const size_t goal = blockIdx.y;
+    const uint4* a = reinterpret_cast<const uint4*>(sim + goal * img_bytes);
+    const uint4* b = reinterpret_cast<const uint4*>(real + goal * real_stride);
+    const size_t n16 = img_bytes / 16;
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 x = a[i], y = __ldg(b + i);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+        uint32_t part = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int sft = 0; sft < 32; sft += 8) {
+                const int d = (int)((xs[k] >> sft) & 0xffu) - (int)((ys[k] >> sft) & 0xffu);
+                part += (uint32_t)(d * d);
+            }
+        }
+        acc += part;
+    }
+    for (size_t i = n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < img_bytes; i += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)sim[goal * img_bytes + i] - (int)real[goal * real_stride + i];
+        acc += (unsigned long long)(d * d);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(RR_FULL, acc, off);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(ssd + goal, acc);
+}
+
+extern "C" cudaError_t rr_launch_score(const uint8_t* sim, const uint8_t* real, size_t img_bytes, size_t real_stride,
+                                       size_t n_goals, unsigned long long* ssd, cudaStream_t st)
+{
+    if (!n_goals) return cudaSuccess;
+    const unsigned chunks = (unsigned)std::min<size_t>(64, (img_bytes / 16 + 255) / 256 + 1);
+    rr_score_kernel<<<dim3(chunks, (unsigned)n_goals), 256, 0, st>>>(sim, real, img_bytes, real_stride, ssd);
+    return cudaGetLastError();
 }
 
 /* raw closest-hit probe (rr_cast_rays) */

@@ -14,7 +14,8 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .types import CastRecord, N_ANGLES, Pose, RadarMaterial, RadarModelConfig, SignalRecord, Stats
+from .types import (CastRecord, N_ANGLES, Pose, RadarMaterial, RadarModel, RadarModelConfig, RadarParams, RadarParamsC,
+                    SignalRecord, Stats)
 
 
 def _ptr(a):
@@ -174,6 +175,59 @@ class RadarB200:
         t, d, n = C.c_float(0), C.c_float(0), C.c_int32(0)
         capi.check(self._ctx, self._lib.rr_kernel_times(self._ctx, C.byref(t), C.byref(d), C.byref(n)))
         return t.value, d.value, n.value
+
+    # ---- GetRadarParams service / GenRadarImage action (srv/GetRadarParams.srv, action/GenRadarImage.action) ----------
+    def getRadarParams(self):
+        """GetRadarParams.srv:1-2 — the RadarParams (materials + model) the next frame would be rendered with."""
+        n = C.c_size_t(0)
+        model = RadarModel()
+        capi.check(self._ctx, self._lib.rr_get_radar_params(self._ctx, None, 0, C.byref(n), C.byref(model)))
+        mats = (RadarMaterial * n.value)()
+        capi.check(self._ctx, self._lib.rr_get_radar_params(self._ctx, mats, n.value, C.byref(n), C.byref(model)))
+        return RadarParams(list(mats), model)
+
+    def genRadarImages(self, goals, Tsm=None, frame_id=None, real=None, return_images=True, out=None):
+        """GenRadarImage.action:1-6, batched: one polar image per goal (RadarParams), each rendered with its own
+        materials, beam_width and n_reflections, from Tsm (one pose for all goals or one per goal; None = last pose).
+        real: optional recorded polar image(s) (n_cells, 400) or (n_goals, n_cells, 400) -> also returns the sum of
+        squared pixel differences per goal, computed on the device (the optimiser's -PSNR data term).
+        Returns images, (images, sse) or sse alone (return_images=False)."""
+        if Tsm is None:
+            if not self.has_last:
+                return None
+            Tsm = self.Tsm_last
+        arr = self._poses(Tsm)
+        goals = list(goals)
+        n = len(goals)
+        carr = (RadarParamsC * n)()
+        keep = []
+        for g, goal in enumerate(goals):
+            m = (RadarMaterial * len(goal.materials))(*goal.materials)
+            keep.append(m)
+            carr[g].materials = C.cast(m, C.POINTER(RadarMaterial))
+            carr[g].n_materials = len(goal.materials)
+            carr[g].model = goal.model
+        if frame_id is None:
+            frame_id = self.frame_counter
+        self.frame_counter = frame_id + n
+        shape = (n, self.m_cfg.n_cells, N_ANGLES)
+        img = None
+        if return_images:
+            img = np.empty(shape, np.uint8) if out is None else out.reshape(shape)
+        sse, real_arr, n_real = None, None, 0
+        if real is not None:
+            real_arr = np.ascontiguousarray(real, np.uint8)
+            n_real = 1 if real_arr.ndim == 2 else real_arr.shape[0]
+            if real_arr.size != n_real * shape[1] * shape[2]:
+                raise ValueError("real must be (n_cells, 400) or (n_goals, n_cells, 400) uint8")
+            sse = np.zeros(n, np.float64)
+        st = Stats()
+        capi.check(self._ctx, self._lib.rr_gen_radar_images(
+            self._ctx, carr, n, arr, len(arr), frame_id, _ptr(img), _ptr(real_arr), n_real, _ptr(sse), C.byref(st)))
+        self.last_stats = st
+        if real is None:
+            return img
+        return (img, sse) if return_images else sse
 
     # ---- parity probes -------------------------------------------------------------------------------------------
     def debug_trace(self, Tsm, frame_id=0, capacity=None):

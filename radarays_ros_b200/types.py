@@ -19,6 +19,23 @@ class RadarModel(C.Structure):
     _fields_ = [("beam_width", C.c_float), ("n_samples", C.c_uint32), ("n_reflections", C.c_uint32)]
 
 
+class RadarParamsC(C.Structure):
+    """rr_radar_params: msg/RadarParams.msg:1-2 as the C ABI takes it (pointer to the material table + model)."""
+    _fields_ = [("materials", C.POINTER(RadarMaterial)), ("n_materials", C.c_uint32), ("model", RadarModel)]
+
+
+class RadarParams:
+    """msg/RadarParams.msg:1-2: `materials` (msg/RadarMaterials.msg: data[]) + `model` (msg/RadarModel.msg).
+    The goal of GenRadarImage.action and the reply of GetRadarParams.srv."""
+
+    def __init__(self, materials, model):
+        self.materials = [m if isinstance(m, RadarMaterial) else RadarMaterial(*m) for m in materials]
+        self.model = RadarModel(model.beam_width, model.n_samples, model.n_reflections)
+
+    def copy(self):
+        return RadarParams([RadarMaterial(m.velocity, m.ambient, m.diffuse, m.specular) for m in self.materials], self.model)
+
+
 _CFG_FIELDS = [
     # (name, ctype, default)  — cfg/RadarModel.cfg:11-85
     ("z_offset", C.c_double, 0.0),
