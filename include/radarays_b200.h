@@ -123,6 +123,16 @@ typedef struct {
     rr_model           model;
 } rr_radar_params;
 
+/* a triangle soup on the host, as rr_set_mesh takes it (owned by the library: release with rr_mesh_free) */
+typedef struct {
+    float*    verts_xyz;       /* n_verts x 3 */
+    size_t    n_verts;
+    uint32_t* tri_idx;         /* n_tris x 3 */
+    size_t    n_tris;
+    uint32_t* tri_object_id;   /* n_tris: scene-graph object of every face (indexes object_materials) */
+    uint32_t  n_objects;
+} rr_mesh;
+
 typedef struct rr_ctx rr_ctx;
 
 int         rr_abi_version(void);
@@ -140,6 +150,13 @@ const char* rr_last_error(const rr_ctx* ctx);                 /* ctx may be NULL
 int         rr_set_mesh(rr_ctx* ctx, const float* verts_xyz, size_t n_verts,
                         const uint32_t* tri_idx, size_t n_tris, const uint32_t* tri_object_id);
 
+/* replaces: the file-reading half of rm::import_embree_map(map_file) (radar_simulator.cpp:149,164; the reference goes
+ * through Rmagine -> assimp). Formats: .ply (ascii / binary, the MulRan map of launch/mulran_sim.launch:7; one mesh ->
+ * object id 0) and .obj (each o/g statement = next object id, for scene graphs like config/oru4.yaml:46-65). Host only,
+ * no context needed. err (nullable) receives a message on failure. rr_set_mesh_file = rr_mesh_load + rr_set_mesh. */
+int         rr_mesh_load(const char* path, rr_mesh* out, char* err, size_t err_capacity);
+void        rr_mesh_free(rr_mesh* mesh);
+int         rr_set_mesh_file(rr_ctx* ctx, const char* path, uint32_t* n_objects_out /* nullable */);
 /* replaces: Radar::loadParams (Radar.cpp:220-226). Bounds-checked (quirk 17). */
 int         rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materials,
                              const int32_t* object_materials, size_t n_objects, int32_t material_id_air);

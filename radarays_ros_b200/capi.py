@@ -14,7 +14,7 @@ SYMBOLS = [
     "rr_set_mesh", "rr_set_materials", "rr_set_params", "rr_set_beam_samples", "rr_get_beam_samples",
     "rr_set_noise_seed", "rr_simulate", "rr_simulate_motion", "rr_simulate_device", "rr_simulate_stats",
     "rr_debug_trace", "rr_cast_rays", "rr_get_stats", "rr_set_max_waves_per_azimuth", "rr_kernel_times", "rr_set_lanes",
-    "rr_get_radar_params", "rr_gen_radar_images",
+    "rr_get_radar_params", "rr_gen_radar_images", "rr_mesh_load", "rr_mesh_free", "rr_set_mesh_file",
 ]
 
 
@@ -56,10 +56,14 @@ def lib():
     L.rr_set_lanes.argtypes = [vp, i32]
     L.rr_get_radar_params.argtypes = [vp, vp, sz, C.POINTER(sz), C.POINTER(RadarModel)]
     L.rr_gen_radar_images.argtypes = [vp, vp, sz, vp, sz, u64, vp, vp, sz, vp, C.POINTER(Stats)]
+    L.rr_mesh_load.argtypes = [C.c_char_p, vp, C.c_char_p, sz]
+    L.rr_mesh_free.argtypes = [vp]
+    L.rr_set_mesh_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32)]
     for name in SYMBOLS:
         getattr(L, name).restype = C.c_int
     L.rr_last_error.restype = C.c_char_p
     L.rr_destroy.restype = None
+    L.rr_mesh_free.restype = None
     L.rr_config_defaults.restype = None
     L.rr_model_defaults.restype = None
     _LIB = L

@@ -400,6 +400,18 @@ int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t*
     return RR_OK;
 }
 
+int rr_set_mesh_file(rr_ctx* ctx, const char* path, uint32_t* n_objects_out)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    rr_mesh m; char msg[400] = {0};
+    int rc = rr_mesh_load(path, &m, msg, sizeof(msg));
+    if (rc) return fail(ctx, rc, "%s", msg);
+    rc = rr_set_mesh(ctx, m.verts_xyz, m.n_verts, m.tri_idx, m.n_tris, m.tri_object_id);
+    if (rc == RR_OK && n_objects_out) *n_objects_out = m.n_objects;
+    rr_mesh_free(&m);
+    return rc;
+}
+
 int rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materials,
                      const int32_t* object_materials, size_t n_objects, int32_t material_id_air)
 {

@@ -14,12 +14,30 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .types import (CastRecord, N_ANGLES, Pose, RadarMaterial, RadarModel, RadarModelConfig, RadarParams, RadarParamsC,
+from .types import (CastRecord, MeshC, N_ANGLES, Pose, RadarMaterial, RadarModel, RadarModelConfig, RadarParams, RadarParamsC,
                     SignalRecord, Stats)
 
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def load_mesh(path):
+    """rm::import_embree_map's file reading (radar_simulator.cpp:149): (verts float32 (V,3), tris uint32 (T,3),
+    tri_object uint32 (T,), n_objects) from a .ply / .obj file, through the C ABI (rr_mesh_load)."""
+    L = capi.lib()
+    m = MeshC()
+    err = C.create_string_buffer(400)
+    rc = L.rr_mesh_load(str(path).encode(), C.byref(m), err, len(err))
+    if rc != 0:
+        raise capi.RadaRaysError(rc, err.value.decode())
+    try:
+        v = np.ctypeslib.as_array(m.verts_xyz, shape=(m.n_verts, 3)).copy()
+        t = np.ctypeslib.as_array(m.tri_idx, shape=(m.n_tris, 3)).copy()
+        o = np.ctypeslib.as_array(m.tri_object_id, shape=(m.n_tris,)).copy()
+        return v, t, o, int(m.n_objects)
+    finally:
+        L.rr_mesh_free(C.byref(m))
 
 
 class RadarB200:
@@ -61,6 +79,13 @@ class RadarB200:
         t = np.ascontiguousarray(tris, np.uint32)
         o = None if tri_object is None else np.ascontiguousarray(tri_object, np.uint32)
         capi.check(self._ctx, self._lib.rr_set_mesh(self._ctx, _ptr(v), v.shape[0], _ptr(t), t.shape[0], _ptr(o)))
+
+    def setMapFile(self, path):
+        """`map_file` of the launch files (launch/mulran_sim.launch:7): read + upload + BVH build; returns the number
+        of scene-graph objects (what `object_materials` must cover)."""
+        n = C.c_uint32(0)
+        capi.check(self._ctx, self._lib.rr_set_mesh_file(self._ctx, str(path).encode(), C.byref(n)))
+        return n.value
 
     def loadParams(self, materials, object_materials, material_id_air=0):
         arr = (RadarMaterial * len(materials))()

@@ -284,3 +284,26 @@ def warehouse(cell=0.165, seed=SEED, n_poses=16, name="warehouse-1M"):
 
 def warehouse_small(seed=SEED):
     return warehouse(cell=0.6, seed=seed, n_poses=4, name="warehouse-small")
+
+
+def write_ply(path, verts, tris, binary=True):
+    """Writes a triangle mesh as .ply (binary_little_endian or ascii) — the format of the reference's MulRan map
+    (launch/mulran_sim.launch:7), so that a synthetic scene can be fed through the file path (rr_set_mesh_file)."""
+    v = np.ascontiguousarray(verts, "<f4").reshape(-1, 3)
+    t = np.ascontiguousarray(tris, "<i4").reshape(-1, 3)
+    hdr = "ply\nformat %s 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n" \
+          "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (
+              "binary_little_endian" if binary else "ascii", len(v), len(t))
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        if binary:
+            f.write(v.tobytes())
+            rec = np.empty(len(t), dtype=[("n", "u1"), ("i", "<i4", 3)])
+            rec["n"] = 3
+            rec["i"] = t
+            f.write(rec.tobytes())
+        else:
+            for p in v:
+                f.write(("%.9g %.9g %.9g\n" % tuple(p)).encode())
+            for tri in t:
+                f.write(("3 %d %d %d\n" % tuple(tri)).encode())

@@ -19,6 +19,12 @@ class RadarModel(C.Structure):
     _fields_ = [("beam_width", C.c_float), ("n_samples", C.c_uint32), ("n_reflections", C.c_uint32)]
 
 
+class MeshC(C.Structure):
+    """rr_mesh: host triangle soup returned by rr_mesh_load."""
+    _fields_ = [("verts_xyz", C.POINTER(C.c_float)), ("n_verts", C.c_size_t), ("tri_idx", C.POINTER(C.c_uint32)),
+                ("n_tris", C.c_size_t), ("tri_object_id", C.POINTER(C.c_uint32)), ("n_objects", C.c_uint32)]
+
+
 class RadarParamsC(C.Structure):
     """rr_radar_params: msg/RadarParams.msg:1-2 as the C ABI takes it (pointer to the material table + model)."""
     _fields_ = [("materials", C.POINTER(RadarMaterial)), ("n_materials", C.c_uint32), ("model", RadarModel)]

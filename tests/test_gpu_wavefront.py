@@ -90,3 +90,20 @@ def test_caller_buffer_and_pinned_output(oracle_mod):
     assert np.array_equal(pageable, ref)
     with pytest.raises(ValueError):
         radar.simulate(poses, frame_id=10, out=np.zeros((5, 768, 400), np.uint8))
+
+
+def test_map_file_equals_arrays(tmp_path):
+    """setMapFile (rr_set_mesh_file: .ply reader + upload + BVH build) renders the same image as the arrays."""
+    sc = scenes.box_room_cylinder()
+    path = tmp_path / "room.ply"
+    scenes.write_ply(path, sc.verts, sc.tris)
+    cfg = RadarModelConfig(n_reflections=2, ambient_noise=2, include_motion=0)
+    a = RadarB200(None, cfg, beam_seed=1, noise_seed=2)
+    assert a.setMapFile(path) == 1
+    a.loadParams(sc.materials, [1], sc.material_id_air)
+    b = RadarB200(None, cfg, beam_seed=1, noise_seed=2)
+    b.setMap(sc.verts, sc.tris, np.zeros(sc.n_tris, np.uint32))
+    b.loadParams(sc.materials, [1], sc.material_id_air)
+    pose = sc.pose_array()[0]
+    img = a.simulate(pose, frame_id=3)
+    assert img.max() > 0 and np.array_equal(img, b.simulate(pose, frame_id=3))

@@ -7,6 +7,6 @@ NV="/usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_1
 for spec in "$@"; do
   tag=${spec%%:*}; flags=${spec#*:}
   $NV $flags -c rr_kernels.cu -o /tmp/rr_kernels_$tag.o
-  $NV -shared -o ../../variants/lib_$tag.so rr_api.o /tmp/rr_kernels_$tag.o rr_bvh_build.o rr_bvh.o -lcudart_static -lpthread -ldl -lrt
+  $NV -shared -o ../../variants/lib_$tag.so rr_api.o /tmp/rr_kernels_$tag.o rr_bvh_build.o rr_bvh.o rr_mesh_io.o -lcudart_static -lpthread -ldl -lrt
   echo built variants/lib_$tag.so "($flags)"
 done
