@@ -142,17 +142,23 @@ __constant__ unsigned char c_perlin_perm[256] = {
 
 /* 2-D slice (z = 0) of the improved-noise function, image_algorithms.h:69-106.
  * With z = 0 the outer blend weight fade(0) is exactly 0, so lerp(w, lower, upper) = lower + 0*(upper-lower)
- * = lower bit-for-bit (upper is finite); only the z-layer-0 gradients are evaluated here. */
-__device__ __forceinline__ double rr_pgrad(int h, double x, double y)
+ * = lower bit-for-bit (upper is finite); only the z-layer-0 gradients are evaluated here.
+ * grad(hash, x, y, 0) (image_algorithms.h:108-128) picks u in {x, y}, v in {y, x, 0} by the low 4 hash bits and returns
+ * (+-u) + (+-v). Every case is cx * x + cy * y with cx, cy in {-1, -0, +0, +1}: the products are exact and a +-0 term
+ * leaves a non-zero partner untouched, so one table lookup + 2 DMUL + 1 DADD replace the chain of predicated selects
+ * bit for bit (only the SIGN of an exact zero result can differ, which fabsf() at RadarCPU.cpp:523 removes). */
+__device__ __forceinline__ double2 rr_pgrad_coef(int h)
 {
     h &= 15;
-    const double u = (h < 8) ? x : y;
-    const double v = (h < 4) ? y : ((h == 12 || h == 14) ? x : 0.0);
-    return ((h & 1) ? -u : u) + ((h & 2) ? -v : v);
+    const double s1 = (h & 1) ? -1.0 : 1.0, s2 = (h & 2) ? -1.0 : 1.0;
+    if (h < 4) return make_double2(s1, s2);                        /* u = x, v = y */
+    if (h < 8) return make_double2(s1, s2 * 0.0);                  /* u = x, v = 0 */
+    if (h == 12 || h == 14) return make_double2(s2, s1);           /* u = y, v = x */
+    return make_double2(s2 * 0.0, s1);                             /* u = y, v = 0 */
 }
 __device__ __forceinline__ double rr_pfade(double t) { return t * t * t * (t * (t * 6 - 15) + 10); }
 __device__ __forceinline__ double rr_plerp(double t, double a, double b) { return a + t * (b - a); }
-__device__ double rr_perlin2(const unsigned char* perm, double sx, double sy)
+__device__ __forceinline__ double rr_perlin2(const unsigned char* perm, const double2* grad, double sx, double sy)
 {
     const double fx = floor(sx), fy = floor(sy);
     const int X = ((int)fx) & 255, Y = ((int)fy) & 255;
@@ -160,8 +166,10 @@ __device__ double rr_perlin2(const unsigned char* perm, double sx, double sy)
     const double u = rr_pfade(x), v = rr_pfade(y);
     const int A = perm[X] + Y, B = perm[(X + 1) & 255] + Y;
     const int AA = perm[A & 255], AB = perm[(A + 1) & 255], BA = perm[B & 255], BB = perm[(B + 1) & 255];
-    const double g00 = rr_pgrad(perm[AA], x, y), g10 = rr_pgrad(perm[BA], x - 1, y);
-    const double g01 = rr_pgrad(perm[AB], x, y - 1), g11 = rr_pgrad(perm[BB], x - 1, y - 1);
+    const double2 c00 = grad[AA], c10 = grad[BA], c01 = grad[AB], c11 = grad[BB];   /* grad[i] = coefficients of perm[i] */
+    const double xm = x - 1, ym = y - 1;
+    const double g00 = c00.x * x + c00.y * y, g10 = c10.x * xm + c10.y * y;
+    const double g01 = c01.x * x + c01.y * ym, g11 = c11.x * xm + c11.y * ym;
     const double lower = rr_plerp(v, rr_plerp(u, g00, g10), rr_plerp(u, g01, g11));
     return lower + 0.0 * 0.0;   /* == lerp(0, lower, upper) */
 }
@@ -554,6 +562,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     extern __shared__ float s_col[];                     /* n_cells floats: this azimuth's range column */
     __shared__ double s_weights[RR_MAX_DENOISE];         /* float weights widened once (the splat multiplies in double) */
     __shared__ unsigned char s_perm[256];
+    __shared__ double2 s_grad[256];
     __shared__ float s_red[RR_WARPS];
     __shared__ uint32_t s_load[RR_MAX_GRANULES];
     __shared__ int s_bound[RR_WARPS + 1];
@@ -566,7 +575,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     const int C = P.n_cells;
     const int n_passes = P.n_passes;
     for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? (double)P.denoise_weights[i] : 0.0;
-    for (int i = tid; i < 256; i += RR_BLOCK) s_perm[i] = c_perlin_perm[i];
+    for (int i = tid; i < 256; i += RR_BLOCK) { s_perm[i] = c_perlin_perm[i]; s_grad[i] = rr_pgrad_coef(c_perlin_perm[i]); }
     const int n_gran = (C + 31) >> 5;                              /* <= 313 for n_cells <= 10000 */
     for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
     for (int i = tid; i < RR_MAX_GRANULES; i += RR_BLOCK) s_load[i] = 0u;
@@ -705,8 +714,8 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
             if (P.ambient_noise == 1) {
                 p = (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 1u + (uint32_t)i);
             } else if (P.ambient_noise == 2) {
-                const double p1 = rr_perlin2(s_perm, random_begin + (double)i * 0.05, ycoord1);
-                const double p2 = rr_perlin2(s_perm, random_begin + (double)i * 0.2, ycoord2);
+                const double p1 = rr_perlin2(s_perm, s_grad, random_begin + (double)i * 0.05, ycoord1);
+                const double p2 = rr_perlin2(s_perm, s_grad, random_begin + (double)i * 0.2, ycoord2);
                 p = 0.9 * p1 + 0.1 * p2;
             }
             const float sn = (float)(1.0 - (double)((v - 0.0f) / signal_amp));
