@@ -70,7 +70,7 @@ def main():
         sc = scenes.warehouse()
         cfg = RadarModelConfig(**dict(MULRAN_DYNCFG, n_cells=3360, n_samples=256, n_reflections=5, resolution=0.02, include_motion=0))
         radar = RadarB200(sc, cfg, beam_seed=20240310, noise_seed=20240310)
-        radar.setMaxWavesPerAzimuth(256 * 32)
+        radar.setMaxWavesPerAzimuth(256 * 10)
         _, st1 = radar.simulate_stats(sc.pose_array()[0])
         ms, s = timed(radar, sc.pose_array())
         print(json.dumps({"config": 4, "mesh": sc.name, "n_tris": sc.n_tris, "passes": 5, "poses": 16, "ms_per_16_frames": ms,
