@@ -644,19 +644,30 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
 
     /* ---- 3. ordered accumulation */
     float m = 0.0f;
+    auto bin_update = [&](const int g, const int st, const float sv, const double svd) {
+        float v;
+        if (P.denoise_on) {
+            v = (float)((double)s_col[g] + svd * s_weights[g - st]);
+        } else {
+            const float old = s_col[g];
+            v = (old < sv) ? sv : old;                                 /* std::max(old, strength), :439 */
+        }
+        s_col[g] = v;
+        if (v > m) m = v;                                              /* running max_val, :428-431 */
+    };
     auto splat = [&](const int st, const float sv) {
         const double svd = (double)sv;
         const int lo = max(max(st, lo_bin), my_lo), hi = min(min(st + W, C), my_hi);
-        for (int g = lo + ((lane - lo) & 31); g < hi; g += 32) {      /* bin g <-> lane g & 31, always */
-            float v;
-            if (P.denoise_on) {
-                v = (float)((double)s_col[g] + svd * s_weights[g - st]);
-            } else {
-                const float old = s_col[g];
-                v = (old < sv) ? sv : old;                             /* std::max(old, strength), :439 */
+        int g = lo + ((lane - lo) & 31);                               /* bin g <-> lane g & 31, always */
+        /* a window of W bins gives a lane 0, 1 or (W > 32) 2.. bins: spelled out so that the common cases cost no loop */
+        if (g < hi) {
+            bin_update(g, st, sv, svd);
+            g += 32;
+            if (g < hi) {
+                bin_update(g, st, sv, svd);
+#pragma unroll 1
+                for (g += 32; g < hi; g += 32) bin_update(g, st, sv, svd);
             }
-            s_col[g] = v;
-            if (v > m) m = v;                                          /* running max_val, :428-431 */
         }
     };
     if (my_lo < my_hi) {
