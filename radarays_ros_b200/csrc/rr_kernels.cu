@@ -90,8 +90,8 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
                                     fmaxf(fmaf(rr_plane(b.y, nz, magic), saz, sbz), 0.0f));
             const float t1f = fminf(fminf(fmaf(rr_plane(a.w, fx, magic), sax, sbx), fmaf(rr_plane(b.x, fy, magic), say, sby)),
                                     fminf(fmaf(rr_plane(b.y, fz, magic), saz, sbz), limit));
-            const bool h0 = (t0n <= t0f) && (b.z != RR_REF_EMPTY);
-            const bool h1 = (t1n <= t1f) && (b.w != RR_REF_EMPTY);
+            const bool h0 = (t0n <= t0f);        /* an absent child (meshes with < 2 leaves) carries an inverted box */
+            const bool h1 = (t1n <= t1f);        /* (rr_bvh_pack), which no ray enters: its ref is never followed */
             if (h0 && h1) {
                 const bool first0 = t0n <= t1n;
                 cur = first0 ? b.z : b.w;
