@@ -59,44 +59,73 @@ def rank_poses(scene, rank, small):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe). The timed region lasts tens of
+    milliseconds, so the sampler reads NVML in-process every 2 ms (nvidia_ml_py); nvidia-smi, one process per sample,
+    is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
-        self.samples = []
+        self.samples = []                    # (sm_mhz, sm_max_mhz, [reason names])
         self.stop_flag = threading.Event()
+        self.source = "nvml"
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = gpu_index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                ids = [int(x) for x in vis.split(",")]
+                if gpu_index < len(ids):
+                    phys = ids[gpu_index]
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self._nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.samples.append((sm, self._max, [n for n, b in bits.items() if mask & b]))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 8:
+            self.samples.append((float(f[1]), float(f[2]), [n for k, n in enumerate(self.NAMES) if f[4 + k].lower().startswith("active")]))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 8:
-                    self.samples.append(f)
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                if self._h is not None:        # NVML hiccup: fall back for the rest of the run
+                    self._h = None
+                    self.source = "nvidia-smi"
+            self.stop_flag.wait(0.002 if self._h is not None else 0.2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for f in self.samples:
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for k, nme in enumerate(names):
-                if f[4 + k].lower().startswith("active"):
-                    reasons.add(nme)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        sm = [x[0] for x in self.samples]
+        reasons = sorted({r for x in self.samples for r in x[2]})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(x[1] for x in self.samples)), "reasons": reasons,
+                "samples": len(sm), "source": self.source}
 
 
 def peak_hbm():
@@ -149,7 +178,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="debug: ~60k-triangle mesh instead of urban-5M")
-    ap.add_argument("--cpu-frames", type=int, default=1, help="frames in the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample (~10 s of host work)")
     ap.add_argument("--lanes", type=int, default=2, help="internal streams per call (rr_set_lanes); 1 = serial launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
