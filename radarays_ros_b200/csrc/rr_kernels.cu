@@ -262,11 +262,13 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                 uint32_t gg = P.first_src[g];
                 while (gbase[gg + 1] <= j) gg++;
                 const size_t slot = (size_t)gg * 64u + (j - gbase[gg]);
-                w.o = rr_v3(cf[0 * sc + slot], cf[1 * sc + slot], cf[2 * sc + slot]);
-                w.d = rr_v3(cf[3 * sc + slot], cf[4 * sc + slot], cf[5 * sc + slot]);
-                w.energy = cd[0 * sc + slot]; w.time = cd[1 * sc + slot];
-                w.mat = cm[slot];
-                item = ci[slot];
+                /* wave state is read once and written once per pass: streaming loads/stores (evict-first) keep the BVH
+                 * nodes and the traversal stacks in L1/L2 instead */
+                w.o = rr_v3(__ldcs(cf + 0 * sc + slot), __ldcs(cf + 1 * sc + slot), __ldcs(cf + 2 * sc + slot));
+                w.d = rr_v3(__ldcs(cf + 3 * sc + slot), __ldcs(cf + 4 * sc + slot), __ldcs(cf + 5 * sc + slot));
+                w.energy = __ldcs(cd + 0 * sc + slot); w.time = __ldcs(cd + 1 * sc + slot);
+                w.mat = __ldcs(cm + slot);
+                item = __ldcs(ci + slot);
             }
             dbg_energy = (float)w.energy;
             /* Tam = Tsm * Tas (RadarCPU.cpp:201-206); Tas.t = 0 */
@@ -390,8 +392,8 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
             }
             /* returns of wave j, in the order RadarCPU.cpp:322,358 appends them; a slot without a return (and a return
              * whose time is not a number, which can not reach a bin either) carries cell INT32_MIN */
-            sg_cell[j] = make_int2((n_sig >= 1) ? sig_cell0 : INT32_MIN, (n_sig >= 2) ? sig_cell1 : INT32_MIN);
-            if (n_sig) sg_str[j] = make_float2(sig_s0, sig_s1);
+            __stcs(sg_cell + j, make_int2((n_sig >= 1) ? sig_cell0 : INT32_MIN, (n_sig >= 2) ? sig_cell1 : INT32_MIN));
+            if (n_sig) __stcs(sg_str + j, make_float2(sig_s0, sig_s1));
             if (DEBUG) {
                 const size_t r0 = (size_t)pass * P.wave_cap + j;
                 rr_cast_record r; r.azimuth = az; r.pass = pass; r.face_id = hit ? face : -1;
@@ -417,18 +419,18 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
             const float skip = 0.001f;                                     /* RadarCPU.cpp:374-378 */
             if (keep0) {
                 const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d0, skip));
-                nf[0 * sc + co] = o2.x; nf[1 * sc + co] = o2.y; nf[2 * sc + co] = o2.z;
-                nf[3 * sc + co] = c_d0.x; nf[4 * sc + co] = c_d0.y; nf[5 * sc + co] = c_d0.z;
-                ndp[0 * sc + co] = c_e0; ndp[1 * sc + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
-                nm[co] = c_m0; ni[co] = item;
+                __stcs(nf + 0 * sc + co, o2.x); __stcs(nf + 1 * sc + co, o2.y); __stcs(nf + 2 * sc + co, o2.z);
+                __stcs(nf + 3 * sc + co, c_d0.x); __stcs(nf + 4 * sc + co, c_d0.y); __stcs(nf + 5 * sc + co, c_d0.z);
+                __stcs(ndp + 0 * sc + co, c_e0); __stcs(ndp + 1 * sc + co, c_time + (double)skip / RR_WAVE_VELOCITY);
+                __stcs(nm + co, c_m0); __stcs(ni + co, item);
                 co++;
             }
             if (keep1) {
                 const rr_vec3 o2 = rr_add(c_o, rr_muls(c_d1, skip));
-                nf[0 * sc + co] = o2.x; nf[1 * sc + co] = o2.y; nf[2 * sc + co] = o2.z;
-                nf[3 * sc + co] = c_d1.x; nf[4 * sc + co] = c_d1.y; nf[5 * sc + co] = c_d1.z;
-                ndp[0 * sc + co] = c_e1; ndp[1 * sc + co] = c_time + (double)skip / RR_WAVE_VELOCITY;
-                nm[co] = c_m1; ni[co] = item;
+                __stcs(nf + 0 * sc + co, o2.x); __stcs(nf + 1 * sc + co, o2.y); __stcs(nf + 2 * sc + co, o2.z);
+                __stcs(nf + 3 * sc + co, c_d1.x); __stcs(nf + 4 * sc + co, c_d1.y); __stcs(nf + 5 * sc + co, c_d1.z);
+                __stcs(ndp + 0 * sc + co, c_e1); __stcs(ndp + 1 * sc + co, c_time + (double)skip / RR_WAVE_VELOCITY);
+                __stcs(nm + co, c_m1); __stcs(ni + co, item);
             }
             if (lane == 0) {                           /* group count + its 1024-group partial sum (rr_scan_kernel) */
                 const uint32_t c = __popc(m0) + __popc(m1);
