@@ -14,5 +14,13 @@ for f in RadarCPU Radar radar_algorithms; do
 done
 $CXX $FLAGS -c "$HERE/ref_harness.cpp" -o "$HERE/_ref/ref_harness.o"
 $CXX -shared -fopenmp -o "$HERE/_ref/libradarays_ref.so" "$HERE/_ref/RadarCPU.o" "$HERE/_ref/Radar.o" "$HERE/_ref/radar_algorithms.o" "$HERE/_ref/ref_harness.o"
-rm -f "$HERE"/_ref/*.o
 echo "built $HERE/_ref/libradarays_ref.so"
+# the reference-side binding (radarays_ros_b200/cpp/RadarB200.hpp) against the reference's own Radar base class
+B200="$HERE/../radarays_ros_b200"
+if [ -f "$B200/libradarays_b200.so" ]; then
+  $CXX $FLAGS -I"$REF/include/radarays_ros" -I"$HERE/../include" -c "$HERE/adapter_harness.cpp" -o "$HERE/_ref/adapter_harness.o"
+  $CXX -shared -fopenmp -o "$HERE/_ref/libradarays_adapter.so" "$HERE/_ref/Radar.o" "$HERE/_ref/adapter_harness.o" \
+      -L"$B200" -lradarays_b200 -Wl,-rpath,'$ORIGIN/../../radarays_ros_b200'
+  echo "built $HERE/_ref/libradarays_adapter.so"
+fi
+rm -f "$HERE"/_ref/*.o

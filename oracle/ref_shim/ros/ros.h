@@ -16,6 +16,7 @@ struct Time {
     Time() = default;
     explicit Time(double s) : sec(s) {}
     static Time now() { return Time(0.0); }
+    uint64_t toNSec() const { return (uint64_t)(sec * 1e9); }
     Duration operator-(const Time& o) const { return Duration{sec - o.sec}; }
     Time operator+(const Duration& d) const { return Time(sec + d.sec); }
 };

@@ -1,8 +1,10 @@
 // RadarB200.hpp — the reference-side binding: a third backend next to RadarCPU / RadarGPU.
 //
 // Drop into uos/radarays_ros as include/radarays_ros/RadarB200.hpp; it needs only the reference's own
-// Radar.hpp (ROS types) and include/radarays_b200.h + libradarays_b200.so from this repo. It is NOT compiled in
-// this repository (no ROS here); INTEGRATION.md shows the three lines of radar_simulator.cpp that select it.
+// Radar.hpp (ROS types) and include/radarays_b200.h + libradarays_b200.so from this repo. INTEGRATION.md shows the
+// three lines of radar_simulator.cpp that select it. In this repository it is compiled against the reference's
+// UNMODIFIED Radar.hpp / Radar.cpp and the ROS stand-ins of oracle/ref_shim (oracle/adapter_harness.cpp ->
+// oracle/_ref/libradarays_adapter.so) and checked on the GPU by tests/test_gpu_adapter.py.
 //
 // Mirrors RadarCPU (include/radarays_ros/RadarCPU.hpp:17-36): same constructor shape, same
 // `sensor_msgs::ImagePtr simulate(ros::Time)` contract — null pointer when TF is unavailable
@@ -44,10 +46,23 @@ public:
     virtual sensor_msgs::ImagePtr simulate(ros::Time stamp)
     {
         sensor_msgs::ImagePtr msg;
-        // include_motion == false: one TF lookup per frame (RadarCPU.cpp:127-134).
-        // include_motion == true : the reference refreshes Tsm per azimuth (RadarCPU.cpp:190-196); the batched
-        // equivalent is 400 interpolated poses passed to rr_simulate_motion (not shown here).
-        if(!updateTsm()) { return msg; }                      // null = "no frame", caller checks (radar_simulator.cpp:88)
+        // include_motion == false: one TF lookup per frame (RadarCPU.cpp:127-134); null = "no frame", the caller
+        // checks (radar_simulator.cpp:88).
+        // include_motion == true : the reference refreshes Tsm before every azimuth (RadarCPU.cpp:190-196) and keeps
+        // the previous pose when a lookup fails; here the 400 lookups happen up front and the 400 poses go to
+        // rr_simulate_motion in one call.
+        const bool motion = m_cfg.include_motion;
+        std::vector<rr_pose> poses;
+        if(!motion) {
+            if(!updateTsm()) { return msg; }
+            poses.push_back(to_pose(Tsm_last));
+        } else {
+            poses.reserve(RR_N_ANGLES);
+            for(int a = 0; a < RR_N_ANGLES; a++) {
+                if(!updateTsm() && !has_last) { return msg; }   // nothing to extrapolate from yet
+                poses.push_back(to_pose(Tsm_last));
+            }
+        }
 
         // materials are re-read every frame by the node (radar_simulator.cpp:85,200): cheap, forward them
         std::vector<rr_material> mats(m_params.materials.data.size());
@@ -79,23 +94,23 @@ public:
         c.ambient_noise_energy_loss = m_cfg.ambient_noise_energy_loss;
         c.scroll_image = m_cfg.scroll_image; c.multipath_threshold = m_cfg.multipath_threshold;
         c.record_multi_reflection = m_cfg.record_multi_reflection; c.record_multi_path = m_cfg.record_multi_path;
-        c.include_motion = 0;
+        c.include_motion = motion ? 1 : 0;
         rr_model model = {(float)m_params.model.beam_width, m_params.model.n_samples, m_params.model.n_reflections};
         check(rr_set_params(m_ctx, &model, &c));             // also applies the m_resample rule (Radar.cpp:199-206)
 
-        const rr_pose Tsm = {Tsm_last.R.x, Tsm_last.R.y, Tsm_last.R.z, Tsm_last.R.w,
-                             Tsm_last.t.x, Tsm_last.t.y, Tsm_last.t.z};
         msg.reset(new sensor_msgs::Image());
         msg->height = m_cfg.n_cells; msg->width = RR_N_ANGLES;  // rows = range bins, cols = azimuths (Radar.cpp:34)
         msg->encoding = sensor_msgs::image_encodings::MONO8; msg->step = RR_N_ANGLES;
         msg->data.resize((size_t)msg->height * msg->width);
-        check(rr_simulate(m_ctx, &Tsm, 1, m_frame_id++, msg->data.data(), nullptr));
+        if(motion) { check(rr_simulate_motion(m_ctx, poses.data(), 1, m_frame_id++, msg->data.data(), nullptr)); }
+        else       { check(rr_simulate(m_ctx, poses.data(), 1, m_frame_id++, msg->data.data(), nullptr)); }
         msg->header.stamp = stamp;
         msg->header.frame_id = m_sensor_frame;
         return msg;
     }
 
 protected:
+    static rr_pose to_pose(const rm::Transform& T) { return rr_pose{T.R.x, T.R.y, T.R.z, T.R.w, T.t.x, T.t.y, T.t.z}; }
     void check(int rc) { if(rc != RR_OK) { throw std::runtime_error(rr_last_error(m_ctx)); } }
     rr_ctx* m_ctx = nullptr;
     uint64_t m_frame_id = 0;
