@@ -36,6 +36,9 @@ public:
               const std::vector<uint32_t>& face_objects, int device = 0)
     : Base(nh_p, tf_buffer, tf_listener, map_frame, sensor_frame)
     {
+        has_last = false;   // Radar.hpp:82 declares `bool has_last;` without an initialiser and Radar.cpp never sets it
+                            // before updateTsm() reads it (Radar.cpp:105): without this, "TF unavailable" on the very
+                            // first frame renders from the identity pose whenever the garbage happens to be non-zero
         check(rr_create(&m_ctx, device));
         check(rr_set_mesh(m_ctx, verts_xyz.data(), verts_xyz.size() / 3, faces.data(), faces.size() / 3,
                           face_objects.empty() ? nullptr : face_objects.data()));

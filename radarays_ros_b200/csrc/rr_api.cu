@@ -652,6 +652,10 @@ struct RRCopyOut { uint8_t* h_dst = nullptr; int n_sub = 0; std::vector<std::pai
  * accumulate over the whole call. `min_split` asks for at least that many sub-batches (pipelining of the copies). */
 static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, int debug, int min_split = 0, RRCopyOut* copy = nullptr)
 {
+    /* The setters upload with cudaMemcpy from pageable memory on the legacy default stream: such a call returns once
+     * the data is staged, possibly before the DMA into device memory has finished, and our streams are non-blocking
+     * (no implicit ordering with the default stream). Wait for those uploads before the kernels can read them. */
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
     CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->d_errflags, 0, 4 * sizeof(int32_t), st));
     const int n_total = P.n_poses;
@@ -1069,6 +1073,7 @@ int rr_cast_rays(rr_ctx* ctx, const float* origins, const float* dirs, size_t n,
     CKD(cudaMalloc((void**)&d_f, n * sizeof(int32_t)));
     CKD(cudaMemcpy(d_o, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
     CKD(cudaMemcpy(d_d, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    CKD(cudaStreamSynchronize(cudaStreamLegacy));          /* pageable uploads are only staged when cudaMemcpy returns */
     CKD(rr_launch_cast(ctx->d_nodes, ctx->d_tris, ctx->root_ref, ctx->grid_origin, ctx->grid_scale, d_o, d_d, n, tmax, d_f, d_r, ctx->stream));
     CKD(cudaStreamSynchronize(ctx->stream));
     CKD(cudaMemcpy(face_ids, d_f, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
