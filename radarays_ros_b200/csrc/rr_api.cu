@@ -25,6 +25,7 @@ extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, u
 int rr_bvh_build_device(const RRTriSoup& soup, RRPackedBVH& out, float* build_ms, std::string& err);   /* rr_bvh_build.cu */
 
 static thread_local std::string g_create_error;
+static const size_t kStatusBytes = 8 * sizeof(unsigned long long) + 4 * sizeof(int32_t);
 
 struct rr_ctx {
     int device = 0;
@@ -69,10 +70,9 @@ struct rr_ctx {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
         float* d_wave_f32 = nullptr; double* d_wave_f64 = nullptr; uint32_t* d_wave_mat = nullptr; uint32_t* d_wave_item = nullptr;
-        uint32_t* d_group_base = nullptr; uint32_t* d_first_src = nullptr; uint32_t* d_item_start = nullptr;
-        uint32_t* d_super = nullptr; uint32_t* d_item_super = nullptr;
+        uint32_t* d_group_base = nullptr; uint32_t* d_first_src = nullptr;
+        uint32_t* d_tables = nullptr;              /* ctrl | item_start | super_count | item_super: zeroed by ONE memset per launch sequence */
         int2* d_sig_cell = nullptr; float2* d_sig_str = nullptr;
-        uint32_t* d_ctrl = nullptr;                /* pass_total[RR_MAX_PASSES + 1] | work_counter[RR_MAX_PASSES] */
     } lanes[kLanes];
     int n_lanes = kLanes;                          /* rr_set_lanes: 1 = serial launches (per-kernel timing) */
     cudaEvent_t fork_ev = nullptr;
@@ -81,7 +81,8 @@ struct rr_ctx {
     uint32_t waves_per_item = 0, wave_cap = 0, max_items = 0;   /* list capacity: per item, per lane; items per launch sequence */
     uint32_t super_stride = 0, item_super_stride = 0;
     uint32_t alloc_passes = 0, alloc_samples = 0;
-    unsigned long long* d_counters = nullptr; int32_t* d_errflags = nullptr;
+    unsigned long long* d_counters = nullptr; int32_t* d_errflags = nullptr;   /* one allocation (kStatusBytes) */
+    unsigned char* h_status = nullptr;             /* pinned copy of it, read back asynchronously by the host path */
     /* host-buffer path staging */
     rr_pose* d_poses = nullptr; size_t d_poses_cap = 0;
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
@@ -252,10 +253,10 @@ static void free_lane_scratch(rr_ctx* ctx)
         rr_ctx::Lane& L = ctx->lanes[l];
         cudaFree(L.d_wave_f32); cudaFree(L.d_wave_f64); cudaFree(L.d_wave_mat); cudaFree(L.d_wave_item);
         cudaFree(L.d_sig_cell); cudaFree(L.d_sig_str); cudaFree(L.d_group_base); cudaFree(L.d_first_src);
-        cudaFree(L.d_item_start); cudaFree(L.d_super); cudaFree(L.d_item_super);
+        cudaFree(L.d_tables);
         L.d_wave_f32 = nullptr; L.d_wave_f64 = nullptr; L.d_wave_mat = nullptr; L.d_wave_item = nullptr;
         L.d_sig_cell = nullptr; L.d_sig_str = nullptr; L.d_group_base = nullptr; L.d_first_src = nullptr;
-        L.d_item_start = nullptr; L.d_super = nullptr; L.d_item_super = nullptr;
+        L.d_tables = nullptr;
     }
     ctx->grid = 0; ctx->max_items = 0;
 }
@@ -313,11 +314,12 @@ int rr_create(rr_ctx** out, int device_id)
     for (int l = 0; l < rr_ctx::kLanes; l++) {
         if ((e = cudaStreamCreateWithFlags(&ctx->lanes[l].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
         if ((e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
-        if ((e = cudaMalloc((void**)&ctx->lanes[l].d_ctrl, (2 * RR_MAX_PASSES + 1) * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     }
     if ((e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if ((e = cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc((void**)&ctx->d_errflags, 4 * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    /* counters[8] (u64) | error_flags[4] (i32): one allocation, one memset per call, one read-back */
+    if ((e = cudaMalloc((void**)&ctx->d_counters, kStatusBytes)) != cudaSuccess) return bail(e, "cudaMalloc");
+    ctx->d_errflags = reinterpret_cast<int32_t*>(ctx->d_counters + 8);
+    if ((e = cudaMallocHost((void**)&ctx->h_status, kStatusBytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
     if ((e = cudaMalloc((void**)&ctx->d_tas, RR_N_ANGLES * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void**)&ctx->d_weights, RR_MAX_DENOISE * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
     /* Tas.R for the 400 azimuths: EulerAngles{0,0,theta(a)}, theta = 0 + a * float(-(2 pi)/400) (Radar.cpp:27-28, RadarCPU.cpp:201-203) */
@@ -343,13 +345,12 @@ void rr_destroy(rr_ctx* ctx)
     cudaFree(ctx->d_weights); cudaFree(ctx->d_noise_decay); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
     free_lane_scratch(ctx);
     for (int l = 0; l < rr_ctx::kLanes; l++) {
-        cudaFree(ctx->lanes[l].d_ctrl);
         if (ctx->lanes[l].done) cudaEventDestroy(ctx->lanes[l].done);
         if (ctx->lanes[l].stream) cudaStreamDestroy(ctx->lanes[l].stream);
     }
     for (cudaEvent_t ev : ctx->sub_ev) cudaEventDestroy(ev);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
-    cudaFree(ctx->d_counters); cudaFree(ctx->d_errflags);
+    cudaFree(ctx->d_counters); if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaFree(ctx->d_poses); cudaFree(ctx->d_out);
     if (ctx->h_poses) cudaFreeHost(ctx->h_poses);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -568,8 +569,9 @@ static int ready(rr_ctx* ctx)
  * items per launch sequence (each lane bounded to ~4 GB of the 180 GB; larger batches run as several sequences). */
 static int ensure_scratch(rr_ctx* ctx, size_t want_items)
 {
-    int per_sm = 0;
-    CK(rr_trace_occupancy(&per_sm));
+    static int per_sm_cached = 0;                 /* a property of the kernel binary and the device type */
+    if (per_sm_cached < 1) CK(rr_trace_occupancy(&per_sm_cached));
+    const int per_sm = per_sm_cached;
     if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "trace kernel does not fit on an SM");
     const int grid = ctx->num_sms * per_sm;
     const uint32_t S = ctx->model.n_samples, Pn = std::max<uint32_t>(1, ctx->model.n_reflections);
@@ -596,9 +598,7 @@ static int ensure_scratch(rr_ctx* ctx, size_t want_items)
             CK(cudaMalloc((void**)&L.d_wave_item, 2 * slot_cap * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_group_base, 2 * (group_cap + 1) * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_first_src, (group_cap + 1) * sizeof(uint32_t)));
-            CK(cudaMalloc((void**)&L.d_item_start, (size_t)(Pn + 1) * (max_items + 1) * sizeof(uint32_t)));
-            CK(cudaMalloc((void**)&L.d_super, (size_t)(Pn + 1) * super_stride * sizeof(uint32_t)));
-            CK(cudaMalloc((void**)&L.d_item_super, (size_t)(Pn + 1) * item_super_stride * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_tables, ((3 * RR_MAX_PASSES + 4) + (size_t)(Pn + 1) * ((max_items + 1) + super_stride + item_super_stride)) * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_sig_cell, (size_t)Pn * wave_cap * sizeof(int2)));
             CK(cudaMalloc((void**)&L.d_sig_str, (size_t)Pn * wave_cap * sizeof(float2)));
         }
@@ -637,10 +637,8 @@ static void bind_lane(rr_ctx* ctx, RRFrameParams& P, int lane)
 {
     const rr_ctx::Lane& L = ctx->lanes[lane];
     P.wave_f32 = L.d_wave_f32; P.wave_f64 = L.d_wave_f64; P.wave_mat = L.d_wave_mat; P.wave_item = L.d_wave_item;
-    P.group_base = L.d_group_base; P.first_src = L.d_first_src; P.item_start = L.d_item_start;
-    P.super_count = L.d_super; P.item_super = L.d_item_super;
+    P.group_base = L.d_group_base; P.first_src = L.d_first_src;
     P.sig_cell = L.d_sig_cell; P.sig_strength = L.d_sig_str;
-    P.pass_total = L.d_ctrl; P.work_counter = L.d_ctrl + (RR_MAX_PASSES + 1);
 }
 
 /* Host-path options of enqueue(): copy every finished sub-batch to `h_dst` on its lane and mark it with an event. */
@@ -656,8 +654,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
      * the data is staged, possibly before the DMA into device memory has finished, and our streams are non-blocking
      * (no implicit ordering with the default stream). Wait for those uploads before the kernels can read them. */
     CK(cudaStreamSynchronize(cudaStreamLegacy));
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(ctx->d_errflags, 0, 4 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, kStatusBytes, st));
     const int n_total = P.n_poses;
     const int n_lanes = (stats || debug) ? 1 : std::max(1, std::min(ctx->n_lanes, (int)rr_ctx::kLanes));
     const int want_split = std::max(min_split, n_lanes);
@@ -696,12 +693,15 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         P.n_items = (int32_t)items;
         P.wave_cap = (uint32_t)((((size_t)items * ctx->waves_per_item) + 31) & ~(size_t)31);
         P.slot_cap = 2 * P.wave_cap; P.group_cap = P.wave_cap / 32; P.item_stride = items + 1;
-        P.super_stride = ctx->super_stride; P.item_super_stride = ctx->item_super_stride;
-        CK(cudaMemsetAsync(ctx->lanes[lane].d_ctrl, 0, (2 * RR_MAX_PASSES + 1) * sizeof(uint32_t), ls));
-        if (Pn > 1) {
-            CK(cudaMemsetAsync(ctx->lanes[lane].d_item_start, 0, (size_t)(Pn + 1) * P.item_stride * sizeof(uint32_t), ls));
-            CK(cudaMemsetAsync(ctx->lanes[lane].d_super, 0, (size_t)(Pn + 1) * P.super_stride * sizeof(uint32_t), ls));
-            CK(cudaMemsetAsync(ctx->lanes[lane].d_item_super, 0, (size_t)(Pn + 1) * P.item_super_stride * sizeof(uint32_t), ls));
+        /* control tables of this launch sequence, compact in the lane's table buffer and zeroed together */
+        P.super_stride = P.group_cap / RR_SCAN_BLOCK + 2; P.item_super_stride = items / RR_SCAN_BLOCK + 2;
+        {
+            uint32_t* t = ctx->lanes[lane].d_tables;
+            P.pass_total = t; P.work_counter = t + (RR_MAX_PASSES + 1); t += 2 * RR_MAX_PASSES + 2;
+            P.item_start = t; t += (size_t)(Pn + 1) * P.item_stride;
+            P.super_count = t; t += (size_t)(Pn + 1) * P.super_stride;
+            P.item_super = t; t += (size_t)(Pn + 1) * P.item_super_stride;
+            CK(cudaMemsetAsync(ctx->lanes[lane].d_tables, 0, (size_t)(t - ctx->lanes[lane].d_tables) * sizeof(uint32_t), ls));
         }
         const uint32_t groups0 = (items * (uint32_t)P.n_samples + 31u) / 32u, warps_per_cta = RR_TRACE_BLOCK / 32;
         const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)ctx->grid, (groups0 + warps_per_cta - 1) / warps_per_cta));
@@ -733,11 +733,27 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
     return RR_OK;
 }
 
+/* read-back of counters + error flags: collect_async() enqueues it on `st` into pinned memory (host path: rides on the
+ * call's final synchronisation), collect() fetches it synchronously; both end in collect_finish() */
+static int collect_async(rr_ctx* ctx, cudaStream_t st)
+{
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->d_counters, kStatusBytes, cudaMemcpyDeviceToHost, st));
+    return RR_OK;
+}
+
+static int collect_finish(rr_ctx* ctx, rr_stats* stats, float kernel_ms);
+
 static int collect(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
 {
+    CK(cudaMemcpy(ctx->h_status, ctx->d_counters, kStatusBytes, cudaMemcpyDeviceToHost));
+    return collect_finish(ctx, stats, kernel_ms);
+}
+
+static int collect_finish(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
+{
     unsigned long long cnt[8]; int32_t flags[4];
-    CK(cudaMemcpy(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(flags, ctx->d_errflags, sizeof(flags), cudaMemcpyDeviceToHost));
+    memcpy(cnt, ctx->h_status, sizeof(cnt));
+    memcpy(flags, ctx->h_status + sizeof(cnt), sizeof(flags));
     rr_stats& s = ctx->last;
     s.n_casts = cnt[0]; s.n_hits = cnt[1]; s.n_signals = cnt[2]; s.nodes_visited = cnt[3]; s.tris_tested = cnt[4];
     s.max_waves = cnt[5]; s.bvh_nodes = ctx->n_nodes;
@@ -790,6 +806,7 @@ static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int
     CK(cudaEventRecord(ctx->ev0, st));
     if ((rc = enqueue(ctx, P, st, with_stats, 0, min_split, &copy))) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
+    if ((rc = collect_async(ctx, st))) return rc;
     for (int k = 0; k < copy.n_sub; k++) {               /* in order: hand every finished sub-batch to the caller */
         CK(cudaEventSynchronize(ctx->sub_ev[k]));
         if (!direct) memcpy(out_polar + (size_t)copy.ranges[k].first * img, ctx->h_out + (size_t)copy.ranges[k].first * img, (size_t)copy.ranges[k].second * img);
@@ -797,7 +814,7 @@ static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    return collect(ctx, stats, ms);
+    return collect_finish(ctx, stats, ms);
 }
 
 int rr_simulate(rr_ctx* ctx, const rr_pose* Tsm, size_t n_poses, uint64_t frame_id0, uint8_t* out_polar, rr_stats* stats)
@@ -957,6 +974,7 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     CK(cudaEventRecord(ctx->ev0, st));
     if ((rc = enqueue(ctx, P, st, 0, 0, min_split, out_polar ? &copy : nullptr))) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
+    if ((rc = collect_async(ctx, st))) return rc;
     std::vector<unsigned long long> ssd(real_polar ? n_goals : 0);
     if (real_polar) {
         CK(rr_launch_score(ctx->d_out, ctx->d_real, img, n_real == 1 ? 0 : img, n_goals, ctx->d_ssd, st));
@@ -973,7 +991,7 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     for (size_t g = 0; g < ssd.size(); g++) sum_sq_err[g] = (double)ssd[g];
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    return collect(ctx, stats, ms);
+    return collect_finish(ctx, stats, ms);
 }
 
 int rr_set_lanes(rr_ctx* ctx, int32_t n_lanes)
@@ -1024,8 +1042,8 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
     CKD(cudaStreamSynchronize(ctx->stream));
     /* the reference's list order: for azimuth, for pass: that azimuth's run of the pass list */
     std::vector<uint32_t> totals(RR_MAX_PASSES + 1), starts((size_t)(Pn + 1) * istride);
-    CKD(cudaMemcpy(totals.data(), ctx->lanes[0].d_ctrl, totals.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CKD(cudaMemcpy(starts.data(), ctx->lanes[0].d_item_start, starts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(totals.data(), ctx->lanes[0].d_tables, totals.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(starts.data(), ctx->lanes[0].d_tables + (2 * RR_MAX_PASSES + 2), starts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     size_t nc = 0, ns = 0;
     std::vector<rr_cast_record> hc; std::vector<rr_signal_record> hs;
     if (casts) { hc.resize(Pn * wcap); CKD(cudaMemcpy(hc.data(), d_casts, hc.size() * sizeof(rr_cast_record), cudaMemcpyDeviceToHost)); }
