@@ -152,7 +152,8 @@ int         rr_set_mesh(rr_ctx* ctx, const float* verts_xyz, size_t n_verts,
 
 /* replaces: the file-reading half of rm::import_embree_map(map_file) (radar_simulator.cpp:149,164; the reference goes
  * through Rmagine -> assimp). Formats: .ply (ascii / binary, the MulRan map of launch/mulran_sim.launch:7; one mesh ->
- * object id 0) and .obj (each o/g statement = next object id, for scene graphs like config/oru4.yaml:46-65). Host only,
+ * object id 0), .obj (each o/g statement = next object id) and .dae (COLLADA scene graph as Blender writes it, the ORU
+ * map of launch/mro_husky.launch:4: every mesh instance = next object id, config/oru4.yaml:46-65). Host only,
  * no context needed. err (nullable) receives a message on failure. rr_set_mesh_file = rr_mesh_load + rr_set_mesh. */
 int         rr_mesh_load(const char* path, rr_mesh* out, char* err, size_t err_capacity);
 void        rr_mesh_free(rr_mesh* mesh);

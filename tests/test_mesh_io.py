@@ -104,7 +104,7 @@ def test_errors_are_reported(tmp_path):
     with pytest.raises(RadaRaysError):
         load_mesh(trunc)
     with pytest.raises(RadaRaysError):
-        load_mesh(tmp_path / "scene.dae")
+        load_mesh(tmp_path / "scene.stl")
 
 
 @pytest.mark.parametrize("binary", [True, False])
@@ -114,3 +114,72 @@ def test_scene_export_round_trip(tmp_path, binary):
     scenes.write_ply(path, sc.verts, sc.tris, binary=binary)
     v, t, o, n_obj = load_mesh(path)
     assert np.array_equal(v, sc.verts) and np.array_equal(t, sc.tris) and n_obj == 1
+
+
+def _dae(geoms, nodes_xml):
+    """geoms: [(id, verts (V,3), prim_xml)] -> COLLADA 1.4 text as Blender lays it out."""
+    out = ['<?xml version="1.0" encoding="utf-8"?>', '<COLLADA xmlns="http://www.collada.org/2005/11/COLLADASchema" version="1.4.1">',
+           '<asset><unit name="meter" meter="1"/><up_axis>Z_UP</up_axis></asset>', '<!-- comment -->', '<library_geometries>']
+    for gid, v, prim in geoms:
+        out.append('<geometry id="%s" name="%s"><mesh>' % (gid, gid))
+        out.append('<source id="%s-positions"><float_array id="%s-positions-array" count="%d">%s</float_array>'
+                   '<technique_common><accessor source="#%s-positions-array" count="%d" stride="3"><param name="X" type="float"/>'
+                   '</accessor></technique_common></source>' % (gid, gid, v.size, " ".join("%.9g" % x for x in v.ravel()), gid, len(v)))
+        out.append('<source id="%s-normals"><float_array id="%s-normals-array" count="3">0 0 1</float_array></source>' % (gid, gid))
+        out.append('<vertices id="%s-vertices"><input semantic="POSITION" source="#%s-positions"/></vertices>' % (gid, gid))
+        out.append(prim % {"g": gid})
+        out.append('</mesh></geometry>')
+    out += ['</library_geometries>', '<library_visual_scenes><visual_scene id="Scene" name="Scene">', nodes_xml,
+            '</visual_scene></library_visual_scenes>', '<scene><instance_visual_scene url="#Scene"/></scene>', '</COLLADA>']
+    return "\n".join(out)
+
+
+def test_dae_scene_graph(tmp_path):
+    sc = scenes.box_room_cylinder()
+    room_t, cyl_t = sc.tris[sc.tri_object == 0], sc.tris[sc.tri_object == 1]
+    cyl_ids = np.unique(cyl_t)
+    remap = {int(i): k for k, i in enumerate(cyl_ids)}
+    cyl_v = sc.verts[cyl_ids]
+    cyl_local = np.array([[remap[int(i)] for i in tri] for tri in cyl_t])
+    # room: <triangles> with VERTEX + NORMAL inputs (stride 2); cylinder: <polylist> of triangles; a quad geometry as <polygons>
+    tri_p = " ".join("%d 0" % i for i in room_t.ravel())
+    prim_room = ('<triangles count="%d"><input semantic="VERTEX" source="#%%(g)s-vertices" offset="0"/>'
+                 '<input semantic="NORMAL" source="#%%(g)s-normals" offset="1"/><p>%s</p></triangles>' % (len(room_t), tri_p))
+    prim_cyl = ('<polylist count="%d"><input semantic="VERTEX" source="#%%(g)s-vertices" offset="0"/><vcount>%s</vcount><p>%s</p></polylist>'
+                % (len(cyl_local), " ".join(["3"] * len(cyl_local)), " ".join(str(i) for i in cyl_local.ravel())))
+    quad_v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    prim_quad = '<polygons count="1"><input semantic="VERTEX" source="#%(g)s-vertices" offset="0"/><p>0 1 2 3</p></polygons>'
+    nodes = ('<node id="Room" type="NODE"><matrix sid="transform">1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1</matrix>'
+             '<instance_geometry url="#Room-mesh"/></node>'
+             '<node id="Group" type="NODE"><translate>1 2 3</translate><rotate>0 0 1 90</rotate><scale>2 2 2</scale>'
+             '<node id="Cyl" type="NODE"><matrix>1 0 0 0.5 0 1 0 0 0 0 1 0 0 0 0 1</matrix><instance_geometry url="#Cyl-mesh"/></node>'
+             '<node id="Quad" type="NODE"><instance_geometry url="#Quad-mesh"/></node></node>')
+    path = tmp_path / "scene.dae"
+    path.write_text(_dae([("Room-mesh", sc.verts, prim_room), ("Cyl-mesh", cyl_v, prim_cyl), ("Quad-mesh", quad_v, prim_quad)], nodes))
+    v, t, o, n_obj = load_mesh(path)
+    assert n_obj == 3 and o.tolist() == [0] * len(room_t) + [1] * len(cyl_t) + [2, 2]
+    nv0 = len(sc.verts)
+    assert np.array_equal(v[:nv0], sc.verts) and np.array_equal(t[:len(room_t)], room_t)
+    # Group = T(1,2,3) * Rz(90 deg) * S(2); Cyl node adds a +0.5 x offset BEFORE the group transform
+    def group(p):
+        q = np.asarray(p, np.float64) * 2.0
+        q = np.stack([-q[:, 1], q[:, 0], q[:, 2]], 1)
+        return q + np.array([1.0, 2.0, 3.0])
+    want_cyl = group(cyl_v.astype(np.float64) + np.array([0.5, 0, 0]))
+    assert np.allclose(v[nv0:nv0 + len(cyl_v)], want_cyl, rtol=0, atol=2e-6)
+    assert np.array_equal(t[len(room_t):len(room_t) + len(cyl_t)], cyl_local + nv0)
+    want_quad = group(quad_v)
+    assert np.allclose(v[nv0 + len(cyl_v):], want_quad, rtol=0, atol=1e-6)
+    q0 = nv0 + len(cyl_v)
+    assert t[-2:].tolist() == [[q0, q0 + 1, q0 + 2], [q0, q0 + 2, q0 + 3]]
+
+
+def test_dae_errors(tmp_path):
+    bad = tmp_path / "bad.dae"
+    bad.write_text("<COLLADA><library_geometries><geometry id='g'><mesh></geometry></COLLADA>")
+    with pytest.raises(RadaRaysError):
+        load_mesh(bad)
+    notdae = tmp_path / "x.dae"
+    notdae.write_text("<html></html>")
+    with pytest.raises(RadaRaysError):
+        load_mesh(notdae)
