@@ -84,7 +84,7 @@ void rr_bvh_build_host(const RRTriSoup& soup, std::vector<RRBuildNode>& nodes, s
             }
             if (best_axis >= 0) {
                 const float area = bb.half_area();
-                if (cnt <= (size_t)RR_MAX_LEAF && (float)cnt * area <= 1.0f * area + best_cost) {
+                if (cnt <= (size_t)RR_MAX_LEAF && (float)cnt * area <= RR_SAH_TRAV_COST * area + best_cost) {
                     split = false;                                   /* leaf is cheaper */
                 } else {
                     const int a = best_axis;

@@ -385,7 +385,7 @@ __global__ void k_small(const SmallNode* __restrict__ small, int n_small, uint32
                 }
             }
             const float area = bb.half_area();
-            if (cnt <= RR_MAX_LEAF && (float)cnt * area <= 1.0f * area + best) split = false;
+            if (cnt <= RR_MAX_LEAF && (float)cnt * area <= RR_SAH_TRAV_COST * area + best) split = false;
         }
         if (split) {
             /* physically order the sub-range along the winning axis (stable insertion sort), left = first best_k */

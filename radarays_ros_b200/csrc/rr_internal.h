@@ -28,7 +28,12 @@ struct __attribute__((aligned(32))) RRNode {
 };
 #define RR_REF_LEAF   0x80000000u
 #define RR_REF_EMPTY  0xffffffffu
+#ifndef RR_MAX_LEAF
 #define RR_MAX_LEAF   4
+#endif
+#ifndef RR_SAH_TRAV_COST
+#define RR_SAH_TRAV_COST 1.0f   /* cost of one node step in units of one triangle test (leaf-vs-split rule of the builders) */
+#endif
 #define RR_STACK_SIZE 64
 
 /* intermediate (full precision) node produced by the builders before packing */
