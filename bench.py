@@ -167,7 +167,8 @@ def cpu_reference_run(scene, cfg, dirs, poses, n_frames, noise_seed):
     obj, kind = cpu_scene(scene)
     t = 0.0
     for i in range(n_frames):
-        t += obj.simulate(cfg, dirs, poses[i:i + 1], noise_seed=noise_seed, frame_id=i, threads=cores)["elapsed_s"]
+        k = i % len(poses)
+        t += obj.simulate(cfg, dirs, poses[k:k + 1], noise_seed=noise_seed, frame_id=i, threads=cores)["elapsed_s"]
     return n_frames / t, kind, cores, t
 
 
