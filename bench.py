@@ -362,7 +362,7 @@ def main():
                          "kernel": "rr_trace_kernel", "kernel_ms": trace_ms_sum / max(n_pairs, 1),
                          "kernel_share_of_step": trace_ms_sum / max(trace_ms_sum + draw_ms_sum, 1e-9),
                          "algorithmic_bytes_per_launch": trace_bytes,
-                         "formula": "32 B x nodes_visited + 48 B x tris_tested + 4 B x hits per 16-pose launch (counted by the stats build of the same kernel)",
+                         "formula": "32 B x nodes_visited + 48 B x tris_tested + 4 B x hits per 16-pose step = the %d per-pass launches of rr_trace_kernel (bytes counted by the stats build of the same kernel; kernel_ms = their summed duration incl. the %d rr_scan_kernel launches between them, CUDA events on the launch stream, one lane)" % (N_PASSES, N_PASSES - 1),
                          "draw_kernel_ms": draw_ms_sum / max(n_pairs, 1), "step_algorithmic_bytes": alg_bytes,
                          "step_achieved_gbs": alg_bytes / ((total_ms / K) / 1000.0) / 1e9,
                          "nodes_visited": nodes, "tris_tested": tris},
