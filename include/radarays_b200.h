@@ -209,6 +209,21 @@ int         rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
 int         rr_cast_rays(rr_ctx* ctx, const float* origins_xyz, const float* dirs_xyz, size_t n,
                          float tmax, int32_t* face_ids, float* ranges);
 
+/* Azimuth-sharded frames on the GPUs of one NVSwitch box WITHOUT a collective library call (one process per GPU):
+ * rank r renders the columns of its azimuth shard and its draw kernel stores every finished mono8 column straight into
+ * the gather buffer of every rank through NVLink peer memory (CUDA IPC); completion flags travel the same way, and each
+ * rank transposes its gather buffer into the full row-major image. No reduction exists on this path (per-column
+ * normalisation, RadarCPU.cpp:156-548), so this is the whole exchange.
+ *   rr_shard_create   allocates this rank's gather buffer (max_poses frames) and returns its IPC handle
+ *   rr_shard_connect  takes the handles of all ranks (rank order, e.g. from an all_gather of the 64-byte handles)
+ *   rr_simulate_sharded  device-resident poses in, the FULL image(s) out on every rank; enqueued on `cuda_stream`,
+ *                     not synchronised. All ranks must call it with the same poses, frame ids and parameters. */
+#define RR_MAX_PEERS 8
+typedef struct { unsigned char opaque[64]; } rr_ipc_handle;
+int         rr_shard_create(rr_ctx* ctx, int32_t rank, int32_t world, size_t max_poses, rr_ipc_handle* handle_out);
+int         rr_shard_connect(rr_ctx* ctx, const rr_ipc_handle* handles /* [world] */);
+int         rr_simulate_sharded(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64_t frame_id0,
+                                uint8_t* d_out_polar, void* cuda_stream);
 int         rr_get_stats(rr_ctx* ctx, rr_stats* stats);       /* counters of the last call */
 
 /* Device time of the two kernels of the path, summed over the launch pairs enqueued since the previous call of this

@@ -16,6 +16,9 @@
 extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats, int debug);
 extern "C" cudaError_t rr_launch_score(const uint8_t* sim, const uint8_t* real, size_t img_bytes, size_t real_stride,
                                        size_t n_goals, unsigned long long* ssd, cudaStream_t st);
+extern "C" cudaError_t rr_launch_peer_exchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch,
+                                               const uint8_t* my_gather, uint8_t* d_out, int n_cells, int scroll, int n_poses,
+                                               int32_t* error_flags, cudaStream_t st);
 extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStream_t st);
 extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
@@ -45,6 +48,12 @@ struct rr_ctx {
     float4* d_materials = nullptr; int32_t* d_object_materials = nullptr;
     int n_materials = 0, n_objects = 0, air = 0;
     std::vector<rr_material> materials_host;      /* for rr_get_radar_params (GetRadarParams.srv) */
+    /* azimuth-sharded frames over peer memory (rr_shard_create / rr_shard_connect / rr_simulate_sharded) */
+    int shard_rank = -1, shard_world = 0;
+    size_t shard_max_poses = 0;
+    uint8_t* shard_base[RR_MAX_PEERS] = {};        /* [flags 256 B | gather buffer 0 | gather buffer 1] of every rank */
+    bool shard_connected = false;
+    uint32_t shard_epoch = 0;
     /* rr_gen_radar_images staging */
     float4* d_goal_mat = nullptr; size_t d_goal_mat_cap = 0;
     float* d_goal_beam = nullptr; size_t d_goal_beam_cap = 0;
@@ -343,6 +352,10 @@ void rr_destroy(rr_ctx* ctx)
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials);
     cudaFree(ctx->d_goal_mat); cudaFree(ctx->d_goal_beam); cudaFree(ctx->d_goal_passes); cudaFree(ctx->d_real); cudaFree(ctx->d_ssd);
     cudaFree(ctx->d_weights); cudaFree(ctx->d_noise_decay); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
+    for (int p = 0; p < ctx->shard_world; p++) {
+        if (!ctx->shard_base[p]) continue;
+        if (p == ctx->shard_rank) cudaFree(ctx->shard_base[p]); else cudaIpcCloseMemHandle(ctx->shard_base[p]);
+    }
     free_lane_scratch(ctx);
     for (int l = 0; l < rr_ctx::kLanes; l++) {
         if (ctx->lanes[l].done) cudaEventDestroy(ctx->lanes[l].done);
@@ -686,6 +699,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         P.poses = poses0 + (size_t)first * (P.pose_per_azimuth ? RR_N_ANGLES : 1);
         P.out = out0 + (size_t)first * out_stride;
         P.frame_id0 = frame0 + (uint64_t)first;
+        P.peer_pose0 = (uint32_t)first;
         P.materials = mat0 + (size_t)first * P.material_stride;
         P.beam_dirs = beam0 + (size_t)first * P.beam_stride;
         P.pose_passes = passes0 ? passes0 + first : nullptr;
@@ -715,7 +729,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
             if (pass + 1 < Pn) { CK(rr_launch_scan(&P, pass + 1, ls)); ctx->launches++; }
         }
         if (timed) CK(cudaEventRecord(te[1], ls));
-        CK(rr_launch_draw(&P, (int)items, (size_t)P.n_cells * sizeof(float), ls, debug));
+        CK(rr_launch_draw(&P, (int)items, (size_t)((P.n_cells + 3) & ~3) * sizeof(float) + (P.n_peers > 0 ? (size_t)P.n_cells : 0), ls, debug));
         ctx->launches++;
         if (timed) { CK(cudaEventRecord(te[2], ls)); ctx->tev_count++; }
         if (copy) {
@@ -728,7 +742,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         CK(cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].stream));
         CK(cudaStreamWaitEvent(st, ctx->lanes[l].done, 0));
     }
-    P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0;
+    P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0; P.peer_pose0 = 0;
     P.materials = mat0; P.beam_dirs = beam0; P.pose_passes = passes0;
     return RR_OK;
 }
@@ -761,6 +775,7 @@ static int collect_finish(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
     s.kernel_ms = kernel_ms; s.bvh_build_ms = ctx->bvh_build_ms; s.overflow = flags[0];
     if (stats) *stats = s;
     if (flags[1]) return fail(ctx, RR_ERR_OUT_OF_RANGE, "a hit face carries an object id >= n_objects");
+    if (flags[2]) return fail(ctx, RR_ERR_CUDA, "rr_simulate_sharded: a peer did not deliver its columns within 5 s");
     if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave list overflow (a pass produced more than %u waves per azimuth on average over a launch); raise rr_set_max_waves_per_azimuth", ctx->waves_per_item);
     return RR_OK;
 }
@@ -992,6 +1007,81 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     return collect_finish(ctx, stats, ms);
+}
+
+/* ---- azimuth-sharded frames over peer memory ------------------------------------------------------------------*/
+static const size_t kShardFlagBytes = 256;
+static const size_t kShardMaxCells = 10000;
+
+int rr_shard_create(rr_ctx* ctx, int32_t rank, int32_t world, size_t max_poses, rr_ipc_handle* handle_out)
+{
+    if (!ctx || !handle_out) return RR_ERR_INVALID_ARGUMENT;
+    if (world < 1 || world > RR_MAX_PEERS || rank < 0 || rank >= world || max_poses < 1)
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_shard_create: rank %d / world %d (max %d) / max_poses %zu", rank, world, RR_MAX_PEERS, max_poses);
+    if (ctx->shard_world) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_shard_create: already created");
+    CK(cudaSetDevice(ctx->device));
+    const size_t half = max_poses * RR_N_ANGLES * kShardMaxCells;
+    uint8_t* base = nullptr;
+    CK(cudaMalloc((void**)&base, kShardFlagBytes + 2 * half));
+    CK(cudaMemset(base, 0, kShardFlagBytes));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, base));
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(rr_ipc_handle), "rr_ipc_handle too small");
+    memset(handle_out, 0, sizeof(*handle_out));
+    memcpy(handle_out, &h, sizeof(h));
+    ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_max_poses = max_poses;
+    ctx->shard_base[rank] = base;
+    return RR_OK;
+}
+
+int rr_shard_connect(rr_ctx* ctx, const rr_ipc_handle* handles)
+{
+    if (!ctx || !handles) return RR_ERR_INVALID_ARGUMENT;
+    if (!ctx->shard_world) return fail(ctx, RR_ERR_NOT_READY, "rr_shard_connect: call rr_shard_create first");
+    if (ctx->shard_connected) return RR_OK;
+    CK(cudaSetDevice(ctx->device));
+    for (int p = 0; p < ctx->shard_world; p++) {
+        if (p == ctx->shard_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &handles[p], sizeof(h));
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->shard_base[p] = (uint8_t*)ptr;
+    }
+    ctx->shard_connected = true;
+    return RR_OK;
+}
+
+int rr_simulate_sharded(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64_t frame_id0, uint8_t* d_out_polar, void* cuda_stream)
+{
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!ctx->shard_world || (ctx->shard_world > 1 && !ctx->shard_connected)) return fail(ctx, RR_ERR_NOT_READY, "rr_simulate_sharded: rr_shard_create / rr_shard_connect first");
+    if (!d_Tsm || !d_out_polar || n_poses == 0 || n_poses > ctx->shard_max_poses)
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_sharded: NULL buffers or n_poses outside [1,%zu]", ctx->shard_max_poses);
+    const int world = ctx->shard_world, rank = ctx->shard_rank;
+    const int base = RR_N_ANGLES / world, extra = RR_N_ANGLES % world;        /* contiguous balanced split (distributed.py) */
+    const int az_begin = rank * base + std::min(rank, extra), az_count = base + (rank < extra ? 1 : 0);
+    if ((rc = ensure_scratch(ctx, n_poses * (size_t)az_count))) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint32_t epoch = ++ctx->shard_epoch;
+    const size_t half = ctx->shard_max_poses * RR_N_ANGLES * kShardMaxCells;
+    RRFrameParams P;
+    fill_params(ctx, P);
+    P.poses = d_Tsm; P.n_poses = (int)n_poses; P.pose_per_azimuth = 0;
+    P.az_begin = az_begin; P.az_count = az_count; P.frame_id0 = frame_id0;
+    P.out = nullptr; P.column_major = 1;
+    P.n_peers = world;
+    uint32_t* flags[RR_MAX_PEERS] = {};
+    for (int p = 0; p < world; p++) {
+        P.peer_out[p] = ctx->shard_base[p] + kShardFlagBytes + (epoch & 1u) * half;
+        flags[p] = reinterpret_cast<uint32_t*>(ctx->shard_base[p]);
+    }
+    if ((rc = enqueue(ctx, P, st, 0, 0))) return rc;
+    CK(rr_launch_peer_exchange(flags, rank, world, epoch, P.peer_out[rank], d_out_polar, P.n_cells, P.scroll_image, (int)n_poses, ctx->d_errflags, st));
+    ctx->launches += 3;
+    return RR_OK;
 }
 
 int rr_set_lanes(rr_ctx* ctx, int32_t n_lanes)

@@ -98,6 +98,12 @@ struct RRFrameParams {
     /* output */
     uint8_t* out;                  /* row-major [pose][cell][400] or column-major [pose][az-az_begin][cell] */
     int32_t column_major;
+    /* azimuth-sharded frames over peer memory (rr_simulate_sharded): when n_peers > 0 the draw kernel stores every
+     * finished column straight into the gather buffer of EVERY rank (NVLink peer stores), column-major over all 400
+     * azimuths: peer_out[p] + ((peer_pose0 + pose) * 400 + azimuth) * n_cells; `out` is not written */
+    uint8_t* peer_out[RR_MAX_PEERS];
+    int32_t n_peers;
+    uint32_t peer_pose0;
     /* wave lists (SoA over slots so that lanes access consecutive words) */
     float* wave_f32;               /* [2 buffers][6 comps][slot_cap] orig.xyz dir.xyz */
     double* wave_f64;              /* [2 buffers][2 comps][slot_cap] energy, time */

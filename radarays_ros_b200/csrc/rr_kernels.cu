@@ -561,7 +561,8 @@ __global__ void __launch_bounds__(RR_SCAN_BLOCK) rr_scan_kernel(const RRFramePar
 template <bool DEBUG>
 __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P)
 {
-    extern __shared__ float s_col[];                     /* n_cells floats: this azimuth's range column */
+    extern __shared__ __align__(16) float s_col[];       /* n_cells floats: this azimuth's range column (+ its mono8 bytes when sharded) */
+    uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_col + ((P.n_cells + 3) & ~3));
     __shared__ double s_weights[RR_MAX_DENOISE];         /* float weights widened once (the splat multiplies in double) */
     __shared__ unsigned char s_perm[256];
     __shared__ double2 s_grad[256];
@@ -742,7 +743,24 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
         v = v * out_scale;
         if (DEBUG && P.dbg_columns) P.dbg_columns[(size_t)az * C + i] = v;
         const uint8_t px = rr_to_u8(v);
-        if (P.column_major) out[i] = px; else out[(size_t)i * RR_N_ANGLES] = px;
+        if (P.n_peers > 0) s_bytes[i] = px;
+        else if (P.column_major) out[i] = px;
+        else out[(size_t)i * RR_N_ANGLES] = px;
+    }
+    if (P.n_peers > 0) {
+        /* the finished mono8 column goes to every rank's gather buffer with 16-byte peer stores (NVLink) */
+        __syncthreads();
+        const size_t col_off = ((size_t)(P.peer_pose0 + (uint32_t)pose_i) * RR_N_ANGLES + (size_t)az) * (size_t)C;
+        for (int p = 0; p < P.n_peers; p++) {
+            uint8_t* dst = P.peer_out[p] + col_off;
+            if (((C & 15) == 0) && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+                const uint4* src4 = reinterpret_cast<const uint4*>(s_bytes);
+                uint4* dst4 = reinterpret_cast<uint4*>(dst);
+                for (int k = tid; k < (C >> 4); k += RR_BLOCK) dst4[k] = src4[k];
+            } else {
+                for (int k = tid; k < C; k += RR_BLOCK) dst[k] = s_bytes[k];
+            }
+        }
     }
 
 }
@@ -790,6 +808,69 @@ extern "C" cudaError_t rr_launch_score(const uint8_t* sim, const uint8_t* real, 
     return cudaGetLastError();
 }
 
+/* ---- azimuth-sharded frames: completion flags over peer memory + local transpose ----------------------------------
+ * rank r, after its draw kernel (whose peer stores are complete when the kernel ends), publishes `epoch` in slot r of
+ * every rank's flag array; a rank may read its gather buffer once all `world` slots of its own array show the epoch. */
+struct RRPeerFlags { uint32_t* flags[RR_MAX_PEERS]; };
+
+__global__ void rr_peer_signal_kernel(const RRPeerFlags F, int rank, int world, uint32_t epoch)
+{
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(F.flags[p] + rank), "r"(epoch) : "memory");
+}
+
+__global__ void rr_peer_wait_kernel(const uint32_t* my_flags, int world, uint32_t epoch, int32_t* error_flags)
+{
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + p) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 5000000000ull) { atomicExch(&error_flags[2], 1); break; }     /* 5 s: a peer never arrived */
+        __nanosleep(200);
+    }
+}
+
+/* gather buffer [pose][400][C] (column-major) -> the reference's image [pose][C][400] with the scroll applied */
+__global__ void __launch_bounds__(256) rr_gather_transpose_kernel(const uint8_t* __restrict__ gather, uint8_t* __restrict__ out,
+                                                                  int C, int scroll)
+{
+    __shared__ uint8_t tile[32][33];
+    const size_t pose = blockIdx.z;
+    const int a0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          /* 32 x 8 threads */
+    const uint8_t* g = gather + pose * (size_t)RR_N_ANGLES * C;
+    uint8_t* o = out + pose * (size_t)C * RR_N_ANGLES;
+    for (int r = ty; r < 32; r += 8) {                                /* rows = azimuths, columns = cells (contiguous) */
+        const int a = a0 + r, c = c0 + tx;
+        tile[r][tx] = (a < RR_N_ANGLES && c < C) ? g[(size_t)a * C + c] : (uint8_t)0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                                /* rows = cells, columns = azimuths (contiguous) */
+        const int c = c0 + r, a = a0 + tx;
+        if (c < C && a < RR_N_ANGLES) o[(size_t)c * RR_N_ANGLES + (scroll + a) % RR_N_ANGLES] = tile[tx][r];
+    }
+}
+
+extern "C" cudaError_t rr_launch_peer_exchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch,
+                                               const uint8_t* my_gather, uint8_t* d_out, int n_cells, int scroll, int n_poses,
+                                               int32_t* error_flags, cudaStream_t st)
+{
+    RRPeerFlags F;
+    for (int p = 0; p < RR_MAX_PEERS; p++) F.flags[p] = p < world ? peer_flags[p] : nullptr;
+    rr_peer_signal_kernel<<<1, 32, 0, st>>>(F, rank, world, epoch);
+    rr_peer_wait_kernel<<<1, 32, 0, st>>>(peer_flags[rank], world, epoch, error_flags);
+    const dim3 grid((unsigned)((n_cells + 31) / 32), (unsigned)((RR_N_ANGLES + 31) / 32), (unsigned)n_poses);
+    rr_gather_transpose_kernel<<<grid, 256, 0, st>>>(my_gather, d_out, n_cells, scroll);
+    return cudaGetLastError();
+}
+
 /* raw closest-hit probe (rr_cast_rays) */
 __global__ void rr_cast_kernel(const RRNode* nodes, const float4* tris, uint32_t root_ref,
                                float gox, float goy, float goz, float gsx, float gsy, float gsz,
@@ -827,6 +908,12 @@ extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStre
 
 extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug)
 {
+    static bool attr_done = false;                     /* 10000 cells + their mono8 bytes (sharded mode) exceed 48 KB with the static tables */
+    if (!attr_done) {
+        cudaFuncSetAttribute(rr_draw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(rr_draw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done = true;
+    }
     if (debug) rr_draw_kernel<true><<<n_items, RR_BLOCK, smem, st>>>(*P);
     else rr_draw_kernel<false><<<n_items, RR_BLOCK, smem, st>>>(*P);
     return cudaGetLastError();

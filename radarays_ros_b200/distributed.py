@@ -8,6 +8,9 @@ return list and its own max_val normalisation (RadarCPU.cpp:156-548), and Perlin
     shard [count][n_cells] (contiguous), one all_gather of uint8 columns (400 x n_cells bytes in total) over
     NCCL/NVLink, then a transpose into the reference's row-major n_cells x 400 image with `scroll_image` applied.
 The collective is torch.distributed (NCCL on GPUs, gloo in the CPU tests of this host logic).
+  * the same frame WITHOUT a collective call (`ShardedRadar(p2p=True)`): the draw kernel of every rank stores its finished
+    columns straight into every rank's gather buffer through NVLink peer memory (CUDA IPC handles exchanged once with
+    all_gather_object), completion flags travel the same way, and each rank transposes locally (rr_simulate_sharded).
 """
 import numpy as np
 
@@ -58,9 +61,29 @@ def gather_frame(local_columns, rank, world, n_cells, scroll_image=0, group=None
 class ShardedRadar:
     """Azimuth-sharded rendering of single frames on `world` GPUs (one process each)."""
 
-    def __init__(self, radar, rank, world, group=None):
+    def __init__(self, radar, rank, world, group=None, p2p=False, max_poses=1):
         self.radar, self.rank, self.world, self.group = radar, rank, world, group
         self.begin, self.count = azimuth_shard(rank, world)
+        self.p2p = p2p
+        if p2p:                                   # one-time exchange of the gather buffers' IPC handles
+            import torch.distributed as dist
+            mine = radar.shardCreate(rank, world, max_poses)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine, group=group)
+            radar.shardConnect(handles)
+            dist.barrier(group=group)
+
+    def simulate_p2p(self, pose, frame_id=0):
+        """Full frame on every rank through peer memory; returns a torch uint8 tensor [n_cells, 400] on the device."""
+        import torch
+        dev = torch.device("cuda", self.radar.device)
+        cfg = self.radar.m_cfg
+        p = np.frombuffer(self.radar._poses(pose), dtype=np.float32).reshape(-1, 7).copy()
+        d_pose = torch.from_numpy(p).to(dev)
+        d_img = torch.empty((cfg.n_cells, N_ANGLES), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        self.radar.simulate_sharded(d_pose.data_ptr(), 1, d_img.data_ptr(), frame_id=frame_id, stream=stream.cuda_stream)
+        return d_img
 
     def simulate(self, pose, frame_id=0):
         import torch

@@ -190,6 +190,24 @@ class RadarB200:
             self._ctx, C.c_void_p(d_poses_ptr), n_poses, frame_id, azimuth_begin, azimuth_count,
             1 if column_major else 0, 1 if pose_per_azimuth else 0, C.c_void_p(d_out_ptr), C.c_void_p(stream)))
 
+    # ---- azimuth-sharded frames over NVLink peer memory (rr_shard_*) ----------------------------------------------------
+    def shardCreate(self, rank, world, max_poses=1):
+        """Allocates this rank's gather buffer; returns its 64-byte CUDA IPC handle (bytes) for the other ranks."""
+        h = C.create_string_buffer(64)
+        capi.check(self._ctx, self._lib.rr_shard_create(self._ctx, rank, world, max_poses, h))
+        return h.raw
+
+    def shardConnect(self, handles):
+        """handles: the IPC handles of all ranks in rank order (this rank's own entry is ignored)."""
+        buf = C.create_string_buffer(b"".join(handles), 64 * len(handles))
+        capi.check(self._ctx, self._lib.rr_shard_connect(self._ctx, buf))
+
+    def simulate_sharded(self, d_poses_ptr, n_poses, d_out_ptr, frame_id=0, stream=0):
+        """Every rank calls this with the same poses: renders its azimuth shard, exchanges columns through peer memory,
+        leaves the FULL row-major image(s) at d_out_ptr on every rank. Enqueued on `stream`, not synchronised."""
+        capi.check(self._ctx, self._lib.rr_simulate_sharded(self._ctx, C.c_void_p(d_poses_ptr), n_poses, frame_id,
+                                                            C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
     def get_stats(self):
         st = Stats()
         capi.check(self._ctx, self._lib.rr_get_stats(self._ctx, C.byref(st)))
