@@ -339,7 +339,7 @@ def main():
             except Exception:
                 traffic = None
         cpu_fps, cpu_kind, cpu_cores, cpu_t = (None, "port", os.cpu_count() or 1, 0.0)
-        if args.cpu_frames > 0:
+        if args.cpu_frames > 0 and world == 1:          # the CPU baseline is timed at N = 1 only (host cores shared by the ranks otherwise)
             cpu_fps, cpu_kind, cpu_cores, cpu_t = cpu_reference_run(scene, cfg, dirs, poses, args.cpu_frames, noise_seed)
         line = {
             "metric": "polar frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -367,7 +367,8 @@ def main():
                          "step_achieved_gbs": alg_bytes / ((total_ms / K) / 1000.0) / 1e9,
                          "nodes_visited": nodes, "tris_tested": tris},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cpu_cores, "kind": cpu_kind,
-                             "sample": "%d frame(s) of the same workload (pose 0..), OpenMP over azimuths, %.1f s" % (args.cpu_frames, cpu_t)},
+                             "sample": ("%d frame(s) of the same workload (pose 0..), OpenMP over azimuths, %.1f s" % (args.cpu_frames, cpu_t))
+                             if cpu_fps is not None else "not timed at N > 1 (see the N = 1 line)"},
         }
         print(json.dumps(line))
     if world > 1:
