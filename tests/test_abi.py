@@ -81,3 +81,20 @@ def test_product_never_imports_the_oracle():
                 code = "\n".join(ln for ln in code.splitlines() if not ln.lstrip().startswith(("#", "//", "*", '"""')) or "#include" in ln)
                 m = pat.search(code)
                 assert not m, "%s references the oracle: %r" % (f, m.group(0))
+
+
+def test_header_is_valid_c99_and_cxx(tmp_path):
+    """include/radarays_b200.h must compile as plain C (the cgo / JNI / ctypes-style binding target) and as C++."""
+    import shutil
+    import subprocess
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include <radarays_b200.h>\nint main(void) { rr_config c; rr_model m; rr_pose p; rr_radar_params g; rr_mesh s; rr_ipc_handle h;'
+                   ' (void)c; (void)m; (void)p; (void)g; (void)s; (void)h; return sizeof(rr_stats) > 0 ? 0 : 1; }\n')
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++17")):
+        if shutil.which(cc) is None:
+            pytest.skip("no %s" % cc)
+        args = [cc, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc]
+        if cc == "g++":
+            args += ["-x", "c++"]
+        subprocess.run(args + [str(src)], check=True)

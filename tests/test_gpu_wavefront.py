@@ -107,3 +107,30 @@ def test_map_file_equals_arrays(tmp_path):
     pose = sc.pose_array()[0]
     img = a.simulate(pose, frame_id=3)
     assert img.max() > 0 and np.array_equal(img, b.simulate(pose, frame_id=3))
+
+
+def test_cpp_example_program(tmp_path):
+    """radarays_ros_b200/cpp/example_render.cpp — the C ABI from plain C++ (map file in, PGM out) — renders the image the
+    Python mirror renders for the same map, parameters and pose."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "radarays_ros_b200", "example_render")
+    if not os.path.exists(exe):
+        pytest.skip("example_render not built (make -C radarays_ros_b200/csrc)")
+    sc = scenes.box_room_cylinder()
+    ply, pgm = tmp_path / "room.ply", tmp_path / "out.pgm"
+    scenes.write_ply(ply, sc.verts, sc.tris)
+    x, y, z, yaw = 1.5, -2.0, 1.0, 0.3
+    out = subprocess.run([exe, str(ply), str(pgm), str(x), str(y), str(z), str(yaw), "3"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "3 frame(s)" in out.stdout
+    data = pgm.read_bytes()
+    cfg = RadarModelConfig(include_motion=0)
+    header = b"P5\n400 %d\n255\n" % cfg.n_cells
+    assert data.startswith(header)
+    img = np.frombuffer(data[len(header):], np.uint8).reshape(cfg.n_cells, 400)
+    radar = RadarB200(None, cfg, beam_seed=1, noise_seed=0)
+    radar.setMapFile(ply)
+    radar.loadParams([(0.3, 1.0, 0.0, 1.0), (0.0, 1.0, 0.0, 3000.0)], [1], 0)
+    want = radar.simulate(Pose.from_xyz_yaw(x, y, z, yaw), frame_id=0)
+    assert np.array_equal(img, want) and img.max() > 0
