@@ -400,6 +400,10 @@ int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t*
     std::string berr;
     const int rc = rr_bvh_build_device(soup, bvh, &build_ms, berr);
     if (rc != RR_OK) return fail(ctx, rc, "rr_set_mesh: BVH build failed: %s", berr.c_str());
+    /* the walk postpones at most one subtree per inner node of the current path: a deeper tree would overflow its stack */
+    if (bvh.max_depth > RR_STACK_SIZE)
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: BVH depth %d exceeds the traversal stack (%d entries)", bvh.max_depth, RR_STACK_SIZE);
+    if (getenv("RR_VERBOSE")) fprintf(stderr, "[rr_set_mesh] %zu triangles, %zu nodes, depth %d, build %.1f ms\n", n_tris, bvh.nodes.size(), bvh.max_depth, build_ms);
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); ctx->d_nodes = nullptr; ctx->d_tris = nullptr;
     CK(cudaMalloc((void**)&ctx->d_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(RRNode)));
     CK(cudaMalloc((void**)&ctx->d_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(float4)));

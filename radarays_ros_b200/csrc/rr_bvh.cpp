@@ -174,13 +174,16 @@ void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& bn, cons
     }
     /* DFS preorder numbering of inner nodes */
     std::vector<int32_t> packed_idx(bn.size(), -1);
-    std::vector<int32_t> stack; stack.push_back(0);
+    std::vector<int32_t> stack, depth; stack.push_back(0); depth.push_back(1);
     int32_t next = 0;
+    out.max_depth = 0;
     while (!stack.empty()) {
         const int32_t i = stack.back(); stack.pop_back();
+        const int32_t d = depth.back(); depth.pop_back();
+        out.max_depth = std::max(out.max_depth, (int)d);
         packed_idx[i] = next++;
-        if (bn[bn[i].right].left >= 0) stack.push_back(bn[i].right);
-        if (bn[bn[i].left].left >= 0) stack.push_back(bn[i].left);
+        if (bn[bn[i].right].left >= 0) { stack.push_back(bn[i].right); depth.push_back(d + 1); }
+        if (bn[bn[i].left].left >= 0) { stack.push_back(bn[i].left); depth.push_back(d + 1); }
     }
     out.nodes.resize(next);
     for (size_t i = 0; i < bn.size(); i++) {

@@ -9,6 +9,7 @@ struct RRPackedBVH {
     std::vector<float4> tris;          /* 3 per triangle, leaf order */
     uint32_t root_ref = 0;
     float grid_origin[3] = {0, 0, 0}, grid_scale[3] = {1, 1, 1};
+    int max_depth = 0;                 /* inner nodes on the longest root-to-leaf path = worst-case traversal stack */
 };
 
 /* per-face (v0, e1, e2) as the kernels and the oracle define them: e1 = v1 - v0, e2 = v2 - v0 in fp32 */
