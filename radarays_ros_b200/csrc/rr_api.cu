@@ -74,7 +74,10 @@ struct rr_ctx {
     /* scratch (wavefront lists, rr_internal.h): one set per LANE. A lane is a stream with its own lists; a call's poses
      * are cut into sub-batches that alternate between the lanes, so the tail of one sub-batch's pass (few long rays left)
      * and its draw kernel overlap the other lane's traversal, and device->host copies overlap compute. */
-    static const int kLanes = 2;
+#ifndef RR_LANES_MAX
+#define RR_LANES_MAX 2
+#endif
+    static const int kLanes = RR_LANES_MAX;
     struct Lane {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -83,7 +86,7 @@ struct rr_ctx {
         uint32_t* d_tables = nullptr;              /* ctrl | item_start | super_count | item_super: zeroed by ONE memset per launch sequence */
         int2* d_sig_cell = nullptr; float2* d_sig_str = nullptr;
     } lanes[kLanes];
-    int n_lanes = kLanes;                          /* rr_set_lanes: 1 = serial launches (per-kernel timing) */
+    int n_lanes = 2;                               /* rr_set_lanes: 1 = serial launches (per-kernel timing) */
     cudaEvent_t fork_ev = nullptr;
     std::vector<cudaEvent_t> sub_ev;               /* one per sub-batch of the host path (copy finished) */
     int grid = 0;
