@@ -8,6 +8,7 @@
 #include <cstring>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rr_bvh.h"
@@ -787,6 +788,23 @@ static int collect_finish(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
     return RR_OK;
 }
 
+/* staging buffer -> pageable caller buffer; above a few MB the copy is cut over 4 threads (a single core moves ~10 GB/s,
+ * which would otherwise cost more than the kernels of a batch) */
+static void host_copy(uint8_t* dst, const uint8_t* src, size_t n)
+{
+    const size_t kMin = (size_t)4 << 20;
+    if (n < kMin) { memcpy(dst, src, n); return; }
+    const int nt = 4;                                  /* measured at 21.5 MB per call: 1 thread 4.7 k, 4: 5.1 k, 8: 5.1 k frames/s (page-locked: 6.8 k) */
+    std::thread th[nt - 1];
+    const size_t part = ((n / nt) + 63) & ~(size_t)63;
+    for (int t = 1; t < nt; t++) {
+        const size_t b = std::min(n, part * t), e = std::min(n, part * (t + 1));
+        th[t - 1] = std::thread([=]() { if (e > b) memcpy(dst + b, src + b, e - b); });
+    }
+    memcpy(dst, src, std::min(n, part));
+    for (int t = 1; t < nt; t++) th[t - 1].join();
+}
+
 /* true if cudaMemcpyAsync can write straight into `p` (page-locked by cudaHostAlloc / cudaHostRegister / torch pin_memory) */
 static bool host_ptr_is_pinned(const void* p)
 {
@@ -831,7 +849,7 @@ static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int
     if ((rc = collect_async(ctx, st))) return rc;
     for (int k = 0; k < copy.n_sub; k++) {               /* in order: hand every finished sub-batch to the caller */
         CK(cudaEventSynchronize(ctx->sub_ev[k]));
-        if (!direct) memcpy(out_polar + (size_t)copy.ranges[k].first * img, ctx->h_out + (size_t)copy.ranges[k].first * img, (size_t)copy.ranges[k].second * img);
+        if (!direct) host_copy(out_polar + (size_t)copy.ranges[k].first * img, ctx->h_out + (size_t)copy.ranges[k].first * img, (size_t)copy.ranges[k].second * img);
     }
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -1006,7 +1024,7 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     if (out_polar) {
         for (int k = 0; k < copy.n_sub; k++) {
             CK(cudaEventSynchronize(ctx->sub_ev[k]));
-            if (!direct) memcpy(out_polar + (size_t)copy.ranges[k].first * img, ctx->h_out + (size_t)copy.ranges[k].first * img, (size_t)copy.ranges[k].second * img);
+            if (!direct) host_copy(out_polar + (size_t)copy.ranges[k].first * img, ctx->h_out + (size_t)copy.ranges[k].first * img, (size_t)copy.ranges[k].second * img);
         }
     }
     CK(cudaStreamSynchronize(st));
