@@ -268,6 +268,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = radar.kernel_launches()
     wall0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for s in range(K):
@@ -279,6 +280,7 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
+    launches_timed = radar.kernel_launches() - launches0      # counted by the library at every <<< >>> of the timed region
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
     img_sum = int(d_out.sum().item())
@@ -353,8 +355,8 @@ def main():
             "casts_per_step": casts, "image_checksum": img_sum,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": POSES_PER_STEP * 28,
                     "d2h_bytes_per_step": POSES_PER_STEP * N_CELLS * N_ANGLES},
-            # per step: rr_trace_kernel once per pass, rr_scan_kernel between passes, rr_draw_kernel
-            "gpu_launches": (2 * N_PASSES) * K,
+            # per launch sequence (one per lane and step): rr_trace_kernel once per pass, rr_scan_kernel between passes, rr_draw_kernel
+            "gpu_launches": int(launches_timed),
             "wall_s_timed_region": wall,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -230,6 +230,9 @@ int         rr_get_stats(rr_ctx* ctx, rr_stats* stats);       /* counters of the
  * function (CUDA events recorded on the launch stream around rr_trace_kernel and rr_draw_kernel; up to 256 pairs are
  * remembered). Synchronises the device. The reference's counterpart is its stdout stopwatch (RadarCPU.cpp:550-553). */
 int         rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_t* n_launch_pairs);
+/* kernels of this library launched through the context since rr_create (trace / scan / draw / score / peer exchange;
+ * the BVH build is not counted): the bench's `gpu_launches` claim. */
+int         rr_kernel_launches(rr_ctx* ctx, uint64_t* n_launches);
 int         rr_set_max_waves_per_azimuth(rr_ctx* ctx, uint32_t max_waves);
 /* replaces: the GetRadarParams service (srv/GetRadarParams.srv:1-2, Radar::getParams Radar.hpp:51-54; called by
  * scripts/radaray_opti.py:135-147). materials_out nullable (size query through n_materials). */

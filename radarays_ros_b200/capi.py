@@ -16,7 +16,7 @@ SYMBOLS = [
     "rr_set_noise_seed", "rr_simulate", "rr_simulate_motion", "rr_simulate_device", "rr_simulate_stats",
     "rr_debug_trace", "rr_cast_rays", "rr_get_stats", "rr_set_max_waves_per_azimuth", "rr_kernel_times", "rr_set_lanes",
     "rr_get_radar_params", "rr_gen_radar_images", "rr_mesh_load", "rr_mesh_free", "rr_set_mesh_file",
-    "rr_shard_create", "rr_shard_connect", "rr_simulate_sharded",
+    "rr_shard_create", "rr_shard_connect", "rr_simulate_sharded", "rr_kernel_launches",
 ]
 
 
@@ -61,6 +61,7 @@ def lib():
     L.rr_shard_create.argtypes = [vp, i32, i32, sz, vp]
     L.rr_shard_connect.argtypes = [vp, vp]
     L.rr_simulate_sharded.argtypes = [vp, vp, sz, u64, vp, vp]
+    L.rr_kernel_launches.argtypes = [vp, C.POINTER(u64)]
     L.rr_mesh_load.argtypes = [C.c_char_p, vp, C.c_char_p, sz]
     L.rr_mesh_free.argtypes = [vp]
     L.rr_set_mesh_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32)]

@@ -1117,6 +1117,13 @@ int rr_set_lanes(rr_ctx* ctx, int32_t n_lanes)
     return RR_OK;
 }
 
+int rr_kernel_launches(rr_ctx* ctx, uint64_t* n_launches)
+{
+    if (!ctx || !n_launches) return RR_ERR_INVALID_ARGUMENT;
+    *n_launches = ctx->launches;
+    return RR_OK;
+}
+
 int rr_get_stats(rr_ctx* ctx, rr_stats* stats)
 {
     if (!ctx || !stats) return RR_ERR_INVALID_ARGUMENT;

@@ -208,6 +208,12 @@ class RadarB200:
         capi.check(self._ctx, self._lib.rr_simulate_sharded(self._ctx, C.c_void_p(d_poses_ptr), n_poses, frame_id,
                                                             C.c_void_p(d_out_ptr), C.c_void_p(stream)))
 
+    def kernel_launches(self):
+        """Kernels launched through this context since it was created."""
+        n = C.c_uint64(0)
+        capi.check(self._ctx, self._lib.rr_kernel_launches(self._ctx, C.byref(n)))
+        return n.value
+
     def get_stats(self):
         st = Stats()
         capi.check(self._ctx, self._lib.rr_get_stats(self._ctx, C.byref(st)))
