@@ -49,7 +49,9 @@ struct RRBuildNode {
 #define RR_BLOCK 128              /* rr_draw_kernel CTA: RR_WARPS warps share one (pose, azimuth) column */
 #endif
 #define RR_WARPS (RR_BLOCK / 32)
+#ifndef RR_TRACE_BLOCK
 #define RR_TRACE_BLOCK 128       /* trace kernel: 4 independent warps per CTA */
+#endif
 #define RR_GROUP 32              /* waves per trace group (= one warp round) */
 #define RR_SCAN_BLOCK 1024       /* rr_scan_kernel: one CTA */
 #define RR_MAX_GRANULES 320      /* ceil(10000 cells / 32) rounded up */
