@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 2
+#define RR_ABI_VERSION 3
 #define RR_N_ANGLES 400            /* Radar.cpp:27-29: theta.size = 400, theta.inc = -(2 pi)/400 */
 
 typedef enum {
@@ -33,7 +33,8 @@ typedef enum {
     RR_ERR_NOT_READY = -3,         /* mesh / materials / params / samples missing */
     RR_ERR_OUT_OF_RANGE = -4,      /* material or object id out of bounds (quirk 17 of SURVEY.md) */
     RR_ERR_WAVE_OVERFLOW = -5,     /* per-azimuth wave list exceeded max_waves_per_azimuth */
-    RR_ERR_NO_DEVICE = -6
+    RR_ERR_NO_DEVICE = -6,
+    RR_ERR_OUT_OF_MEMORY = -7      /* host allocation failed / a size in the input is absurd; no C++ exception ever crosses this ABI */
 } rr_status;
 
 /* msg/RadarMaterial.msg:1-4 */
@@ -164,7 +165,10 @@ int         rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n
 
 /* replaces: Radar::updateDynCfg (Radar.cpp:188-218) + Radar::setParams (Radar.hpp:56-59).
  * `model` nullable -> derived from cfg exactly as updateDynCfg does. Marks beam samples for resampling
- * under the same conditions (Radar.cpp:199-206). */
+ * under the same conditions (Radar.cpp:199-206). Every field is checked against its [min, max] of
+ * cfg/RadarModel.cfg:11-85 (what dynamic_reconfigure clamps to before updateDynCfg runs; n_samples may go up to 65535);
+ * a rejected call changes nothing. Setters must not be called while an un-synchronised rr_simulate_device /
+ * rr_simulate_sharded call is still running on the device. */
 int         rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg);
 
 /* replaces: sample_cone_local (radar_algorithms.cpp:248-294) cached in m_waves_start (RadarCPU.cpp:136-145).

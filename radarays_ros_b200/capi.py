@@ -8,7 +8,7 @@ from .types import RadarModel, RadarModelConfig, Stats
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RADARAYS_B200_LIB", os.path.join(_HERE, "libradarays_b200.so"))   # override: tuning builds
 _LIB = None
-ABI_VERSION = 2          # RR_ABI_VERSION of include/radarays_b200.h this binding was written against
+ABI_VERSION = 3          # RR_ABI_VERSION of include/radarays_b200.h this binding was written against
 
 SYMBOLS = [
     "rr_abi_version", "rr_config_defaults", "rr_model_defaults", "rr_create", "rr_destroy", "rr_last_error",

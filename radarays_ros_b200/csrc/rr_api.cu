@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 #include <chrono>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -21,6 +23,8 @@ extern "C" cudaError_t rr_launch_peer_exchange(uint32_t* const* peer_flags, int 
                                                const uint8_t* my_gather, uint8_t* d_out, int n_cells, int scroll, int n_poses,
                                                int32_t* error_flags, cudaStream_t st);
 extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStream_t st);
+extern "C" cudaError_t rr_launch_prep(const RRFrameParams* P, cudaStream_t st);
+extern "C" cudaError_t rr_launch_mat_pairs(const float4* materials, int n_mat, int n_tables, RRMatPair* out, cudaStream_t st);
 extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
@@ -47,7 +51,9 @@ struct rr_ctx {
     /* materials */
     bool have_materials = false;
     float4* d_materials = nullptr; int32_t* d_object_materials = nullptr;
+    RRMatPair* d_mat_pairs = nullptr;              /* [n_materials + 1] Snell/Fresnel constants per far-side medium (rr_mat_pairs_kernel) */
     int n_materials = 0, n_objects = 0, air = 0;
+    cudaEvent_t upload_ev = nullptr;               /* last setter upload on `stream`; every launch sequence waits for it */
     std::vector<rr_material> materials_host;      /* for rr_get_radar_params (GetRadarParams.srv) */
     /* azimuth-sharded frames over peer memory (rr_shard_create / rr_shard_connect / rr_simulate_sharded) */
     int shard_rank = -1, shard_world = 0;
@@ -57,6 +63,7 @@ struct rr_ctx {
     uint32_t shard_epoch = 0;
     /* rr_gen_radar_images staging */
     float4* d_goal_mat = nullptr; size_t d_goal_mat_cap = 0;
+    RRMatPair* d_goal_pairs = nullptr; size_t d_goal_pairs_cap = 0;
     float* d_goal_beam = nullptr; size_t d_goal_beam_cap = 0;
     int32_t* d_goal_passes = nullptr; size_t d_goal_passes_cap = 0;
     uint8_t* d_real = nullptr; size_t d_real_cap = 0;
@@ -86,6 +93,7 @@ struct rr_ctx {
         uint32_t* d_group_base = nullptr; uint32_t* d_first_src = nullptr;
         uint32_t* d_tables = nullptr;              /* ctrl | item_start | super_count | item_super: zeroed by ONE memset per launch sequence */
         int2* d_sig_cell = nullptr; float2* d_sig_str = nullptr;
+        float4* d_item_xf = nullptr;               /* [max_items][3] item transforms (rr_prep_kernel) */
     } lanes[kLanes];
     int n_lanes = 2;                               /* rr_set_lanes: 1 = serial launches (per-kernel timing) */
     cudaEvent_t fork_ev = nullptr;
@@ -116,6 +124,15 @@ static int fail(rr_ctx* c, int code, const char* fmt, ...)
     if (c) c->err = buf; else g_create_error = buf;
     return code;
 }
+/* no C++ exception may cross the C ABI: every extern "C" entry point is a function-try-block ending here */
+static int guard(rr_ctx* ctx, const char* fn)
+{
+    try { throw; }
+    catch (const std::bad_alloc&) { return fail(ctx, RR_ERR_OUT_OF_MEMORY, "%s: out of host memory", fn); }
+    catch (const std::length_error& e) { return fail(ctx, RR_ERR_OUT_OF_MEMORY, "%s: size too large (%s)", fn, e.what()); }
+    catch (const std::exception& e) { return fail(ctx, RR_ERR_INVALID_ARGUMENT, "%s: %s", fn, e.what()); }
+    catch (...) { return fail(ctx, RR_ERR_INVALID_ARGUMENT, "%s: unknown exception", fn); }
+}
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, RR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 template <typename T> static cudaError_t regrow(T** p, size_t* cap, size_t need, bool pinned = false)
@@ -125,6 +142,18 @@ template <typename T> static cudaError_t regrow(T** p, size_t* cap, size_t need,
     cudaError_t e = pinned ? cudaMallocHost((void**)p, need * sizeof(T)) : cudaMalloc((void**)p, need * sizeof(T));
     *cap = (e == cudaSuccess) ? need : 0;
     return e;
+}
+
+/* Setter uploads travel on the context's own stream and leave an event that every launch sequence waits for (the launch
+ * streams are non-blocking, i.e. not ordered with the legacy default stream, and a cudaMemcpy from pageable memory may
+ * return before its DMA has landed). cudaMemcpyAsync from pageable memory returns once the source is staged, so the
+ * caller's buffer may be reused at once. */
+static cudaError_t upload(rr_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!bytes) return cudaSuccess;
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(ctx->upload_ev, ctx->stream);
 }
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -266,7 +295,7 @@ static void free_lane_scratch(rr_ctx* ctx)
         rr_ctx::Lane& L = ctx->lanes[l];
         cudaFree(L.d_wave_f32); cudaFree(L.d_wave_f64); cudaFree(L.d_wave_mat); cudaFree(L.d_wave_item);
         cudaFree(L.d_sig_cell); cudaFree(L.d_sig_str); cudaFree(L.d_group_base); cudaFree(L.d_first_src);
-        cudaFree(L.d_tables);
+        cudaFree(L.d_tables); cudaFree(L.d_item_xf); L.d_item_xf = nullptr;
         L.d_wave_f32 = nullptr; L.d_wave_f64 = nullptr; L.d_wave_mat = nullptr; L.d_wave_item = nullptr;
         L.d_sig_cell = nullptr; L.d_sig_str = nullptr; L.d_group_base = nullptr; L.d_first_src = nullptr;
         L.d_tables = nullptr;
@@ -303,7 +332,7 @@ void rr_model_defaults(rr_model* m)
 
 const char* rr_last_error(const rr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int rr_create(rr_ctx** out, int device_id)
+int rr_create(rr_ctx** out, int device_id) try
 {
     rr_ctx* ctx = nullptr;
     if (!out) return fail(nullptr, RR_ERR_INVALID_ARGUMENT, "rr_create: out is NULL");
@@ -329,6 +358,7 @@ int rr_create(rr_ctx** out, int device_id)
         if ((e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
     if ((e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->upload_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     /* counters[8] (u64) | error_flags[4] (i32): one allocation, one memset per call, one read-back */
     if ((e = cudaMalloc((void**)&ctx->d_counters, kStatusBytes)) != cudaSuccess) return bail(e, "cudaMalloc");
     ctx->d_errflags = reinterpret_cast<int32_t*>(ctx->d_counters + 8);
@@ -342,11 +372,12 @@ int rr_create(rr_ctx** out, int device_id)
         const rr_quat q = euler_to_quat(0.0f, 0.0f, 0.0f + (float)a * theta_inc);
         tas[a] = make_float4(q.x, q.y, q.z, q.w);
     }
-    if ((e = cudaMemcpy(ctx->d_tas, tas.data(), tas.size() * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    if ((e = upload(ctx, ctx->d_tas, tas.data(), tas.size() * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMemcpy");
     rr_config_defaults(&ctx->cfg);
     *out = ctx;
     return RR_OK;
 }
+catch (...) { return guard(nullptr, "rr_create"); }
 
 void rr_destroy(rr_ctx* ctx)
 {
@@ -354,6 +385,7 @@ void rr_destroy(rr_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials);
+    cudaFree(ctx->d_mat_pairs); cudaFree(ctx->d_goal_pairs);
     cudaFree(ctx->d_goal_mat); cudaFree(ctx->d_goal_beam); cudaFree(ctx->d_goal_passes); cudaFree(ctx->d_real); cudaFree(ctx->d_ssd);
     cudaFree(ctx->d_weights); cudaFree(ctx->d_noise_decay); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
     for (int p = 0; p < ctx->shard_world; p++) {
@@ -367,6 +399,7 @@ void rr_destroy(rr_ctx* ctx)
     }
     for (cudaEvent_t ev : ctx->sub_ev) cudaEventDestroy(ev);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);
     cudaFree(ctx->d_counters); if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaFree(ctx->d_poses); cudaFree(ctx->d_out);
     if (ctx->h_poses) cudaFreeHost(ctx->h_poses);
@@ -379,7 +412,7 @@ void rr_destroy(rr_ctx* ctx)
 }
 
 int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t* tri_idx, size_t n_tris,
-                const uint32_t* tri_object_id)
+                const uint32_t* tri_object_id) try
 {
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     if ((n_tris && (!verts || !tri_idx)) || n_tris >= (1u << 28))
@@ -413,6 +446,7 @@ int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t*
     CK(cudaMalloc((void**)&ctx->d_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(float4)));
     CK(cudaMemcpy(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(RRNode), cudaMemcpyHostToDevice));
     if (!bvh.tris.empty()) CK(cudaMemcpy(ctx->d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());                         /* a pageable cudaMemcpy may return before its DMA has landed */
     ctx->n_nodes = bvh.nodes.size(); ctx->n_tris = n_tris; ctx->root_ref = bvh.root_ref;
     memcpy(ctx->grid_origin, bvh.grid_origin, sizeof(ctx->grid_origin));
     memcpy(ctx->grid_scale, bvh.grid_scale, sizeof(ctx->grid_scale));
@@ -421,8 +455,9 @@ int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t*
     ctx->have_mesh = true;
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_set_mesh"); }
 
-int rr_set_mesh_file(rr_ctx* ctx, const char* path, uint32_t* n_objects_out)
+int rr_set_mesh_file(rr_ctx* ctx, const char* path, uint32_t* n_objects_out) try
 {
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     rr_mesh m; char msg[400] = {0};
@@ -433,9 +468,10 @@ int rr_set_mesh_file(rr_ctx* ctx, const char* path, uint32_t* n_objects_out)
     rr_mesh_free(&m);
     return rc;
 }
+catch (...) { return guard(ctx, "rr_set_mesh_file"); }
 
 int rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materials,
-                     const int32_t* object_materials, size_t n_objects, int32_t material_id_air)
+                     const int32_t* object_materials, size_t n_objects, int32_t material_id_air) try
 {
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     if (!materials || !n_materials || !object_materials || !n_objects)
@@ -448,27 +484,68 @@ int rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materia
     CK(cudaSetDevice(ctx->device));
     std::vector<float4> m(n_materials);
     for (size_t i = 0; i < n_materials; i++) m[i] = make_float4(materials[i].velocity, materials[i].ambient, materials[i].diffuse, materials[i].specular);
-    cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials); ctx->d_materials = nullptr; ctx->d_object_materials = nullptr;
+    ctx->have_materials = false;
+    cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials); cudaFree(ctx->d_mat_pairs);      /* cudaFree waits for the device */
+    ctx->d_materials = nullptr; ctx->d_object_materials = nullptr; ctx->d_mat_pairs = nullptr;
     CK(cudaMalloc((void**)&ctx->d_materials, n_materials * sizeof(float4)));
     CK(cudaMalloc((void**)&ctx->d_object_materials, n_objects * sizeof(int32_t)));
-    CK(cudaMemcpy(ctx->d_materials, m.data(), n_materials * sizeof(float4), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_object_materials, object_materials, n_objects * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&ctx->d_mat_pairs, (n_materials + 1) * sizeof(RRMatPair)));
+    CK(upload(ctx, ctx->d_materials, m.data(), n_materials * sizeof(float4)));
+    CK(upload(ctx, ctx->d_object_materials, object_materials, n_objects * sizeof(int32_t)));
+    CK(rr_launch_mat_pairs(ctx->d_materials, (int)n_materials, 1, ctx->d_mat_pairs, ctx->stream));
+    CK(cudaEventRecord(ctx->upload_ev, ctx->stream));
     ctx->n_materials = (int)n_materials; ctx->n_objects = (int)n_objects; ctx->air = material_id_air;
     ctx->materials_host.assign(materials, materials + n_materials);
     ctx->have_materials = true;
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_set_materials"); }
 
-int rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg)
+/* cfg/RadarModel.cfg:11-85 gives every parameter a [min, max]; dynamic_reconfigure clamps to it before
+ * Radar::updateDynCfg ever sees a value. A C caller has no such filter, so out-of-range (or NaN) values are rejected
+ * here, BEFORE anything of the context is touched: a failed call leaves the previous parameter set fully in place. */
+static const char* config_range_error(const rr_config& c, char* buf, size_t n)
+{
+    struct D { const char* name; double v, lo, hi; };
+    const D dd[] = {
+        {"z_offset", c.z_offset, -2.0, 2.0}, {"range_min", c.range_min, 0.0, 10.0}, {"range_max", c.range_max, 0.0, 1000.0},
+        {"beam_width", c.beam_width, 0.0, 90.0}, {"resolution", c.resolution, 0.0, 3.0},
+        {"beam_sample_dist_normal_p_in_cone", c.beam_sample_dist_normal_p_in_cone, 0.0, 0.999},
+        {"energy_min", c.energy_min, 0.0, 1.0}, {"energy_max", c.energy_max, 0.0, 1.0}, {"signal_max", c.signal_max, 0.0, 255.0},
+        {"signal_denoising_triangular_mode", c.signal_denoising_triangular_mode, 0.0, 1.0},
+        {"signal_denoising_gaussian_mode", c.signal_denoising_gaussian_mode, 0.0, 1.0},
+        {"signal_denoising_mb_mode", c.signal_denoising_mb_mode, 0.0, 1.0},
+        {"ambient_noise_at_signal_0", c.ambient_noise_at_signal_0, 0.0, 1.0}, {"ambient_noise_at_signal_1", c.ambient_noise_at_signal_1, 0.0, 1.0},
+        {"ambient_noise_energy_max", c.ambient_noise_energy_max, 0.0, 1.0}, {"ambient_noise_energy_min", c.ambient_noise_energy_min, 0.0, 1.0},
+        {"ambient_noise_energy_loss", c.ambient_noise_energy_loss, 0.0, 1.0}, {"ambient_noise_uniform_max", c.ambient_noise_uniform_max, 0.0, 1.0},
+        {"ambient_noise_perlin_scale_low", c.ambient_noise_perlin_scale_low, 0.0, 1.0},
+        {"ambient_noise_perlin_scale_high", c.ambient_noise_perlin_scale_high, 0.0, 1.0},
+        {"ambient_noise_perlin_p_low", c.ambient_noise_perlin_p_low, 0.0, 1.0}, {"multipath_threshold", c.multipath_threshold, 0.0, 1.0},
+    };
+    for (const D& d : dd)
+        if (!(d.v >= d.lo && d.v <= d.hi)) { snprintf(buf, n, "%s = %g outside [%g, %g] (cfg/RadarModel.cfg)", d.name, d.v, d.lo, d.hi); return buf; }
+    struct I { const char* name; long v, lo, hi; };
+    const I ii[] = {
+        {"n_cells", c.n_cells, 1, 10000}, {"n_samples", c.n_samples, 1, 65535 /* cfg: 10000; the lists hold up to 65535 */},
+        {"beam_sample_dist", c.beam_sample_dist, 0, 3}, {"n_reflections", c.n_reflections, 0, 20},
+        {"signal_denoising", c.signal_denoising, 0, 3},
+        {"signal_denoising_triangular_width", c.signal_denoising_triangular_width, 1, 200},
+        {"signal_denoising_gaussian_width", c.signal_denoising_gaussian_width, 1, 200},
+        {"signal_denoising_mb_width", c.signal_denoising_mb_width, 1, 200},
+        {"ambient_noise", c.ambient_noise, 0, 2}, {"scroll_image", c.scroll_image, 0, 400},
+    };
+    for (const I& d : ii)
+        if (d.v < d.lo || d.v > d.hi) { snprintf(buf, n, "%s = %ld outside [%ld, %ld] (cfg/RadarModel.cfg)", d.name, d.v, d.lo, d.hi); return buf; }
+    if (!(c.resolution > 0.0)) { snprintf(buf, n, "resolution must be > 0"); return buf; }
+    return nullptr;
+}
+
+int rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg) try
 {
     if (!ctx || !cfg) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_params: cfg is NULL");
-    if (cfg->n_cells < 1 || cfg->n_cells > 10000) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "n_cells %d outside [1,10000]", cfg->n_cells);
-    const int dn = cfg->signal_denoising;
-    const int width = dn == 1 ? cfg->signal_denoising_triangular_width : dn == 2 ? cfg->signal_denoising_gaussian_width
-                    : dn == 3 ? cfg->signal_denoising_mb_width : 1;
-    if (dn < 0 || dn > 3 || width < 1 || width > 200) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "signal_denoising %d / width %d invalid", dn, width);
-    if (cfg->ambient_noise < 0 || cfg->ambient_noise > 2) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "ambient_noise %d invalid", cfg->ambient_noise);
-    if (!(cfg->resolution > 0.0)) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "resolution must be > 0");
+    /* ---- 1. validate everything; nothing of ctx is modified before the last check has passed */
+    char msg[200];
+    if (config_range_error(*cfg, msg, sizeof(msg))) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_params: %s", msg);
     rr_model m;
     if (model) m = *model;
     else {   /* Radar.cpp:209-215 */
@@ -478,38 +555,41 @@ int rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg)
     }
     if (m.n_samples < 1 || m.n_samples > 65535) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "n_samples %u outside [1,65535]", m.n_samples);
     if (m.n_reflections > 20) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "n_reflections %u > 20", m.n_reflections);
+    if (!(m.beam_width >= 0.0f && m.beam_width <= 3.2f)) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "model.beam_width %g rad outside [0, pi]", (double)m.beam_width);
+    std::vector<float> w; int mode = 0;
+    build_denoise_weights(*cfg, w, mode);
+    if (cfg->signal_denoising > 0 && (mode < 0 || mode >= (int)w.size()))
+        return fail(ctx, RR_ERR_INVALID_ARGUMENT, "denoising mode index %d outside kernel width %zu", mode, w.size());
+    /* range attenuation of the ambient noise floor, exp(-loss * x_i) with x_i the centre of cell i (RadarCPU.cpp:517-521):
+     * depends on the parameters only, so it is tabulated here once with the same rr_detmath.h routine the kernels use
+     * (bit-identical on host and device) instead of being re-evaluated for every cell of every column. */
+    const int C = cfg->n_cells;
+    std::vector<float> decay((size_t)C);
+    const float e_loss = (float)cfg->ambient_noise_energy_loss;
+    for (int i = 0; i < C; i++) {
+        const float x = (float)(((double)(float)i + 0.5) * cfg->resolution);
+        decay[i] = rr_expf(-e_loss * x);
+    }
+    std::vector<float> wpad(RR_MAX_DENOISE, 0.f);
+    std::copy(w.begin(), w.end(), wpad.begin());
+    /* ---- 2. device side (a failing CUDA call is not a parameter error: the device state is then undefined anyway) */
     CK(cudaSetDevice(ctx->device));
-    /* Radar.cpp:199-206: which changes invalidate the cached beam samples */
+    if ((size_t)C > ctx->d_noise_decay_cap) CK(cudaDeviceSynchronize());          /* regrow frees the table a running launch may read */
+    CK(regrow(&ctx->d_noise_decay, &ctx->d_noise_decay_cap, (size_t)C));
+    CK(upload(ctx, ctx->d_weights, wpad.data(), RR_MAX_DENOISE * sizeof(float)));
+    CK(upload(ctx, ctx->d_noise_decay, decay.data(), (size_t)C * sizeof(float)));
+    /* ---- 3. commit. Radar.cpp:199-206: which changes invalidate the cached beam samples */
     if (!ctx->have_params || cfg->beam_sample_dist != ctx->cfg.beam_sample_dist
         || std::fabs(cfg->beam_width - ctx->cfg.beam_width) > 0.001 || cfg->n_samples != ctx->cfg.n_samples
         || std::fabs(cfg->beam_sample_dist_normal_p_in_cone - ctx->cfg.beam_sample_dist_normal_p_in_cone) > 0.001
         || m.n_samples != ctx->model.n_samples || m.beam_width != ctx->model.beam_width)
         ctx->resample = true;
     ctx->cfg = *cfg; ctx->model = m;
-    std::vector<float> w; int mode = 0;
-    build_denoise_weights(*cfg, w, mode);
-    if (dn > 0 && (mode < 0 || mode >= (int)w.size())) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "denoising mode index %d outside kernel width %zu", mode, w.size());
-    std::vector<float> wpad(RR_MAX_DENOISE, 0.f);
-    std::copy(w.begin(), w.end(), wpad.begin());
-    CK(cudaMemcpy(ctx->d_weights, wpad.data(), RR_MAX_DENOISE * sizeof(float), cudaMemcpyHostToDevice));
     ctx->denoise_width = (int)w.size(); ctx->denoise_mode = mode;
-    /* range attenuation of the ambient noise floor, exp(-loss * x_i) with x_i the centre of cell i (RadarCPU.cpp:517-521):
-     * depends on the parameters only, so it is tabulated here once with the same rr_detmath.h routine the kernels use
-     * (bit-identical on host and device) instead of being re-evaluated for every cell of every column. */
-    {
-        const int C = std::max(cfg->n_cells, 1);
-        std::vector<float> decay((size_t)C);
-        const float e_loss = (float)cfg->ambient_noise_energy_loss;
-        for (int i = 0; i < C; i++) {
-            const float x = (float)(((double)(float)i + 0.5) * cfg->resolution);
-            decay[i] = rr_expf(-e_loss * x);
-        }
-        CK(regrow(&ctx->d_noise_decay, &ctx->d_noise_decay_cap, (size_t)C));
-        CK(cudaMemcpy(ctx->d_noise_decay, decay.data(), (size_t)C * sizeof(float), cudaMemcpyHostToDevice));
-    }
     ctx->have_params = true;
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_set_params"); }
 
 int rr_set_noise_seed(rr_ctx* ctx, uint64_t seed) { if (!ctx) return RR_ERR_INVALID_ARGUMENT; ctx->noise_seed = seed; return RR_OK; }
 
@@ -528,11 +608,11 @@ static int upload_beam(rr_ctx* ctx)
         CK(cudaMalloc((void**)&ctx->d_beam, n * 3 * sizeof(float)));
         ctx->d_beam_n = n;
     }
-    CK(cudaMemcpy(ctx->d_beam, ctx->beam.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    CK(upload(ctx, ctx->d_beam, ctx->beam.data(), n * 3 * sizeof(float)));
     return RR_OK;
 }
 
-int rr_set_beam_samples(rr_ctx* ctx, const float* dirs_xyz, size_t n, uint64_t seed)
+int rr_set_beam_samples(rr_ctx* ctx, const float* dirs_xyz, size_t n, uint64_t seed) try
 {
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(ctx->device));
@@ -546,6 +626,7 @@ int rr_set_beam_samples(rr_ctx* ctx, const float* dirs_xyz, size_t n, uint64_t s
     ctx->beam_user = false; ctx->resample = true;      /* drawn when the parameters are known */
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_set_beam_samples"); }
 
 static int ensure_beam(rr_ctx* ctx)
 {
@@ -558,7 +639,7 @@ static int ensure_beam(rr_ctx* ctx)
     return upload_beam(ctx);
 }
 
-int rr_get_beam_samples(rr_ctx* ctx, float* out, size_t capacity, size_t* n_out)
+int rr_get_beam_samples(rr_ctx* ctx, float* out, size_t capacity, size_t* n_out) try
 {
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     if (!ctx->have_params) return fail(ctx, RR_ERR_NOT_READY, "rr_get_beam_samples: rr_set_params first");
@@ -572,6 +653,7 @@ int rr_get_beam_samples(rr_ctx* ctx, float* out, size_t capacity, size_t* n_out)
     }
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_get_beam_samples"); }
 
 /* ---- launch plumbing ------------------------------------------------------------------------------------*/
 static int ready(rr_ctx* ctx)
@@ -622,6 +704,7 @@ static int ensure_scratch(rr_ctx* ctx, size_t want_items)
             CK(cudaMalloc((void**)&L.d_tables, ((3 * RR_MAX_PASSES + 4) + (size_t)(Pn + 1) * ((max_items + 1) + super_stride + item_super_stride)) * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_sig_cell, (size_t)Pn * wave_cap * sizeof(int2)));
             CK(cudaMalloc((void**)&L.d_sig_str, (size_t)Pn * wave_cap * sizeof(float2)));
+            CK(cudaMalloc((void**)&L.d_item_xf, (size_t)max_items * 3 * sizeof(float4)));
         }
         ctx->grid = grid; ctx->waves_per_item = wpi; ctx->alloc_passes = Pn; ctx->alloc_samples = S;
         ctx->wave_cap = (uint32_t)wave_cap; ctx->max_items = (uint32_t)max_items;
@@ -636,7 +719,7 @@ static void fill_params(rr_ctx* ctx, RRFrameParams& P)
     const rr_config& c = ctx->cfg;
     P.nodes = ctx->d_nodes; P.tris = ctx->d_tris; P.root_ref = ctx->root_ref;
     for (int a = 0; a < 3; a++) { P.grid_origin[a] = ctx->grid_origin[a]; P.grid_scale[a] = ctx->grid_scale[a]; }
-    P.materials = ctx->d_materials; P.object_materials = ctx->d_object_materials;
+    P.materials = ctx->d_materials; P.object_materials = ctx->d_object_materials; P.mat_pairs = ctx->d_mat_pairs;
     P.n_materials = ctx->n_materials; P.n_objects = ctx->n_objects; P.material_id_air = ctx->air;
     P.beam_dirs = ctx->d_beam; P.tas_quat = ctx->d_tas;
     P.n_samples = (int)ctx->model.n_samples; P.n_passes = (int)ctx->model.n_reflections;
@@ -659,7 +742,7 @@ static void bind_lane(rr_ctx* ctx, RRFrameParams& P, int lane)
     const rr_ctx::Lane& L = ctx->lanes[lane];
     P.wave_f32 = L.d_wave_f32; P.wave_f64 = L.d_wave_f64; P.wave_mat = L.d_wave_mat; P.wave_item = L.d_wave_item;
     P.group_base = L.d_group_base; P.first_src = L.d_first_src;
-    P.sig_cell = L.d_sig_cell; P.sig_strength = L.d_sig_str;
+    P.sig_cell = L.d_sig_cell; P.sig_strength = L.d_sig_str; P.item_xf = L.d_item_xf;
 }
 
 /* Host-path options of enqueue(): copy every finished sub-batch to `h_dst` on its lane and mark it with an event. */
@@ -671,10 +754,8 @@ struct RRCopyOut { uint8_t* h_dst = nullptr; int n_sub = 0; std::vector<std::pai
  * accumulate over the whole call. `min_split` asks for at least that many sub-batches (pipelining of the copies). */
 static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, int debug, int min_split = 0, RRCopyOut* copy = nullptr)
 {
-    /* The setters upload with cudaMemcpy from pageable memory on the legacy default stream: such a call returns once
-     * the data is staged, possibly before the DMA into device memory has finished, and our streams are non-blocking
-     * (no implicit ordering with the default stream). Wait for those uploads before the kernels can read them. */
-    CK(cudaStreamSynchronize(cudaStreamLegacy));
+    /* setter uploads (upload()) are ordered before everything this call launches */
+    CK(cudaStreamWaitEvent(st, ctx->upload_ev, 0));
     CK(cudaMemsetAsync(ctx->d_counters, 0, kStatusBytes, st));
     const int n_total = P.n_poses;
     const int n_lanes = (stats || debug) ? 1 : std::max(1, std::min(ctx->n_lanes, (int)rr_ctx::kLanes));
@@ -685,6 +766,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
     uint8_t* out0 = P.out;
     const uint64_t frame0 = P.frame_id0;
     const float4* mat0 = P.materials; const float* beam0 = P.beam_dirs; const int32_t* passes0 = P.pose_passes;
+    const RRMatPair* pairs0 = P.mat_pairs;
     const size_t out_stride = P.column_major ? (size_t)P.az_count * P.n_cells : (size_t)P.n_cells * RR_N_ANGLES;
     const int Pn = P.n_passes;
     const int n_sub = (n_total + poses_per_launch - 1) / poses_per_launch;
@@ -709,6 +791,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         P.frame_id0 = frame0 + (uint64_t)first;
         P.peer_pose0 = (uint32_t)first;
         P.materials = mat0 + (size_t)first * P.material_stride;
+        P.mat_pairs = pairs0 + (size_t)first * P.mat_pair_stride;
         P.beam_dirs = beam0 + (size_t)first * P.beam_stride;
         P.pose_passes = passes0 ? passes0 + first : nullptr;
         const uint32_t items = (uint32_t)n * (uint32_t)P.az_count;
@@ -729,6 +812,8 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)ctx->grid, (groups0 + warps_per_cta - 1) / warps_per_cta));
         const bool timed = ctx->tev_count < rr_ctx::kRing;
         cudaEvent_t* te = ctx->tev[timed ? ctx->tev_count : 0];
+        CK(rr_launch_prep(&P, ls));
+        ctx->launches++;
         if (timed) CK(cudaEventRecord(te[0], ls));
         for (int pass = 0; pass < Pn; pass++) {
             /* later lists can be up to 2^pass times longer than list 0: keep the full persistent grid for them */
@@ -751,7 +836,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         CK(cudaStreamWaitEvent(st, ctx->lanes[l].done, 0));
     }
     P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0; P.peer_pose0 = 0;
-    P.materials = mat0; P.beam_dirs = beam0; P.pose_passes = passes0;
+    P.materials = mat0; P.beam_dirs = beam0; P.pose_passes = passes0; P.mat_pairs = pairs0;
     return RR_OK;
 }
 
@@ -857,25 +942,28 @@ static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int
     return collect_finish(ctx, stats, ms);
 }
 
-int rr_simulate(rr_ctx* ctx, const rr_pose* Tsm, size_t n_poses, uint64_t frame_id0, uint8_t* out_polar, rr_stats* stats)
+int rr_simulate(rr_ctx* ctx, const rr_pose* Tsm, size_t n_poses, uint64_t frame_id0, uint8_t* out_polar, rr_stats* stats) try
 {
     return simulate_host(ctx, Tsm, n_poses, 0, frame_id0, out_polar, stats, 0);
 }
+catch (...) { return guard(ctx, "rr_simulate"); }
 
 int rr_simulate_motion(rr_ctx* ctx, const rr_pose* Tsm_per_azimuth, size_t n_frames, uint64_t frame_id0,
-                       uint8_t* out_polar, rr_stats* stats)
+                       uint8_t* out_polar, rr_stats* stats) try
 {
     return simulate_host(ctx, Tsm_per_azimuth, n_frames, 1, frame_id0, out_polar, stats, 0);
 }
+catch (...) { return guard(ctx, "rr_simulate_motion"); }
 
-int rr_simulate_stats(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0, uint8_t* out_polar, rr_stats* stats)
+int rr_simulate_stats(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0, uint8_t* out_polar, rr_stats* stats) try
 {
     return simulate_host(ctx, Tsm, 1, 0, frame_id0, out_polar, stats, 1);
 }
+catch (...) { return guard(ctx, "rr_simulate_stats"); }
 
 int rr_simulate_device(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64_t frame_id0,
                        int32_t azimuth_begin, int32_t azimuth_count, int32_t column_major,
-                       int32_t pose_per_azimuth, uint8_t* d_out_polar, void* cuda_stream)
+                       int32_t pose_per_azimuth, uint8_t* d_out_polar, void* cuda_stream) try
 {
     int rc = ready(ctx);
     if (rc) return rc;
@@ -891,6 +979,7 @@ int rr_simulate_device(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64
     P.out = d_out_polar; P.column_major = column_major ? 1 : 0;
     return enqueue(ctx, P, (cudaStream_t)cuda_stream, 0, 0);
 }
+catch (...) { return guard(ctx, "rr_simulate_device"); }
 
 int rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_t* n_launch_pairs)
 {
@@ -912,7 +1001,7 @@ int rr_kernel_times(rr_ctx* ctx, float* trace_ms_sum, float* draw_ms_sum, int32_
 }
 
 /* GetRadarParams.srv (srv/GetRadarParams.srv:1-2): the RadarParams the next frame would be rendered with */
-int rr_get_radar_params(rr_ctx* ctx, rr_material* materials_out, size_t capacity, size_t* n_materials, rr_model* model_out)
+int rr_get_radar_params(rr_ctx* ctx, rr_material* materials_out, size_t capacity, size_t* n_materials, rr_model* model_out) try
 {
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     if (!ctx->have_materials || !ctx->have_params) return fail(ctx, RR_ERR_NOT_READY, "rr_get_radar_params: materials / params not set");
@@ -924,12 +1013,13 @@ int rr_get_radar_params(rr_ctx* ctx, rr_material* materials_out, size_t capacity
     if (model_out) *model_out = ctx->model;
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_get_radar_params"); }
 
 /* GenRadarImage.action (action/GenRadarImage.action:1-6), batched: goal g = RadarParams -> polar image g, rendered from
  * Tsm[g] (or Tsm[0]). Every goal keeps its own material table, beam bundle (beam_width) and pass count in one launch. */
 int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goals, const rr_pose* Tsm, size_t n_poses,
                         uint64_t frame_id0, uint8_t* out_polar, const uint8_t* real_polar, size_t n_real,
-                        double* sum_sq_err, rr_stats* stats)
+                        double* sum_sq_err, rr_stats* stats) try
 {
     int rc = ready(ctx);
     if (rc) return rc;
@@ -1033,12 +1123,13 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     return collect_finish(ctx, stats, ms);
 }
+catch (...) { return guard(ctx, "rr_gen_radar_images"); }
 
 /* ---- azimuth-sharded frames over peer memory ------------------------------------------------------------------*/
 static const size_t kShardFlagBytes = 256;
 static const size_t kShardMaxCells = 10000;
 
-int rr_shard_create(rr_ctx* ctx, int32_t rank, int32_t world, size_t max_poses, rr_ipc_handle* handle_out)
+int rr_shard_create(rr_ctx* ctx, int32_t rank, int32_t world, size_t max_poses, rr_ipc_handle* handle_out) try
 {
     if (!ctx || !handle_out) return RR_ERR_INVALID_ARGUMENT;
     if (world < 1 || world > RR_MAX_PEERS || rank < 0 || rank >= world || max_poses < 1)
@@ -1059,8 +1150,9 @@ int rr_shard_create(rr_ctx* ctx, int32_t rank, int32_t world, size_t max_poses, 
     ctx->shard_base[rank] = base;
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_shard_create"); }
 
-int rr_shard_connect(rr_ctx* ctx, const rr_ipc_handle* handles)
+int rr_shard_connect(rr_ctx* ctx, const rr_ipc_handle* handles) try
 {
     if (!ctx || !handles) return RR_ERR_INVALID_ARGUMENT;
     if (!ctx->shard_world) return fail(ctx, RR_ERR_NOT_READY, "rr_shard_connect: call rr_shard_create first");
@@ -1077,8 +1169,9 @@ int rr_shard_connect(rr_ctx* ctx, const rr_ipc_handle* handles)
     ctx->shard_connected = true;
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_shard_connect"); }
 
-int rr_simulate_sharded(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64_t frame_id0, uint8_t* d_out_polar, void* cuda_stream)
+int rr_simulate_sharded(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint64_t frame_id0, uint8_t* d_out_polar, void* cuda_stream) try
 {
     int rc = ready(ctx);
     if (rc) return rc;
@@ -1108,6 +1201,7 @@ int rr_simulate_sharded(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint6
     ctx->launches += 3;
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_simulate_sharded"); }
 
 int rr_set_lanes(rr_ctx* ctx, int32_t n_lanes)
 {
@@ -1135,7 +1229,7 @@ int rr_get_stats(rr_ctx* ctx, rr_stats* stats)
 int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
                    rr_cast_record* casts, size_t cast_capacity, size_t* n_casts,
                    rr_signal_record* signals, size_t signal_capacity, size_t* n_signals,
-                   float* columns_f32, uint8_t* out_polar)
+                   float* columns_f32, uint8_t* out_polar) try
 {
     int rc = ready(ctx);
     if (rc) return rc;
@@ -1154,7 +1248,7 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
     CKD(cudaMalloc((void**)&d_cols, (size_t)RR_N_ANGLES * C * sizeof(float)));
     CKD(cudaMalloc((void**)&d_pose, sizeof(rr_pose)));
     CKD(cudaMalloc((void**)&d_img, (size_t)C * RR_N_ANGLES));
-    CKD(cudaMemcpy(d_pose, Tsm, sizeof(rr_pose), cudaMemcpyHostToDevice));
+    CKD(upload(ctx, d_pose, Tsm, sizeof(rr_pose)));
     RRFrameParams P;
     fill_params(ctx, P);
     P.poses = d_pose; P.n_poses = 1; P.pose_per_azimuth = 0; P.az_begin = 0; P.az_count = RR_N_ANGLES;
@@ -1196,8 +1290,9 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
 #undef CKD
     return collect(ctx, nullptr, 0.f);
 }
+catch (...) { return guard(ctx, "rr_debug_trace"); }
 
-int rr_cast_rays(rr_ctx* ctx, const float* origins, const float* dirs, size_t n, float tmax, int32_t* face_ids, float* ranges)
+int rr_cast_rays(rr_ctx* ctx, const float* origins, const float* dirs, size_t n, float tmax, int32_t* face_ids, float* ranges) try
 {
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     if (!ctx->have_mesh) return fail(ctx, RR_ERR_NOT_READY, "no mesh: call rr_set_mesh");
@@ -1222,5 +1317,6 @@ int rr_cast_rays(rr_ctx* ctx, const float* origins, const float* dirs, size_t n,
 #undef CKD
     return RR_OK;
 }
+catch (...) { return guard(ctx, "rr_cast_rays"); }
 
 } // extern "C"

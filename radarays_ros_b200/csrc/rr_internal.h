@@ -43,6 +43,18 @@ struct RRBuildNode {
     int32_t first, count;    /* leaf range in the ordered primitive array */
 };
 
+/* ---- per-launch tables that keep per-ray shading short --------------------------------------------
+ * Everything in the wave model that depends only on the (pose, azimuth) item or only on the pair of media at a surface
+ * is evaluated ONCE by a prologue kernel with the very same rr_detmath.h routines the per-ray code used to call, so the
+ * bits are those of the per-ray evaluation (RadarCPU.cpp:201-209 for the item pose; radar_algorithms.h:60-63,80-90,110
+ * for the media pair). The wave velocity is the constant 0.3 (quirk kept, rr_kernels.cu), so n2 = 0.3 always. */
+struct __attribute__((aligned(32))) RRMatPair {
+    double n1;           /* (double)(float) velocity of the far-side medium (RadarCPU.cpp:273-280)       */
+    double th_limit;     /* asin(n2/n1) when |n2/n1| <= 1, else 100 (radar_algorithms.h:82-88); unused when n1 <= 0 */
+    double n12;          /* n1 / n2 (radar_algorithms.h:98)                                              */
+    double rs0;          /* (n1 - n2) / (n1 + n2): rs = rp at normal incidence (radar_algorithms.h:110)  */
+};
+
 /* ---- kernel parameter block ---------------------------------------------------------------------*/
 #define RR_MAX_DENOISE 256
 #ifndef RR_BLOCK
@@ -75,6 +87,9 @@ struct RRFrameParams {
     uint32_t material_stride;      /* 0 = one table for all poses; n_materials = one table per goal (rr_gen_radar_images) */
     const int32_t* object_materials;
     int32_t n_materials, n_objects, material_id_air;
+    const RRMatPair* mat_pairs;    /* [n_materials + 1] per table: entry id = far-side medium; entry n_materials = "same medium on both sides" */
+    uint32_t mat_pair_stride;      /* 0 = one table for all poses; n_materials + 1 = one table per goal */
+    float4* item_xf;               /* [n_items][2]: Tam = Tsm * Tas of the item: (R.x,R.y,R.z,R.w), (T.x,T.y,T.z,0); written by rr_prep_kernel */
     /* beam + poses */
     const float* beam_dirs;        /* n_samples x 3; pose p reads beam_dirs + p * beam_stride */
     uint32_t beam_stride;          /* 0 = one bundle for all poses; 3 * n_samples = one bundle per goal */

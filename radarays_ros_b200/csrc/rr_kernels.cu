@@ -33,6 +33,22 @@ __device__ __noinline__ rr_vec3 rr_normalize_ol(rr_vec3 v) { return rr_normalize
 /* rr_tan_of (rr_detmath.h:111) with its one division out of line: (-c)/s or s/c */
 __device__ __forceinline__ double rr_tan_of_ol(rr_sincos_t p) { return RR_DDIV((p.q & 1) ? -p.c : p.s, (p.q & 1) ? p.s : p.c); }
 
+/* (float)acos(0.0f) as the reference's acos(float) gives it (radar_algorithms.h:106 with a zero refraction vector) */
+#define RR_ACOSF_OF_ZERO 1.57079637050628662109375f
+
+/* back_reflection_shader (radar_algorithms.h:168-187) without the incoming energy: A + B * pow(cos(angle), C) with
+ * (A, B, C) = (ambient, diffuse, specular). With a lobe factor B = +-0 (config/mulran_kaist02.yaml:15-18 and most of the
+ * reference's material files) the lobe only contributes the SIGN of a zero as long as it is finite: for angle < pi/2 the
+ * cosine is a float in (0, 1] (no float equals pi/2, so it never rounds to 0), and pow of that with an exponent C >= 0 is
+ * a finite value >= +0, hence B * lobe = B (as +-0) exactly. Everything else takes the full evaluation. */
+__device__ __forceinline__ float rr_brdf(float angle, float4 mt)
+{
+    float term;
+    if (mt.z == 0.0f && mt.w >= 0.0f && (double)angle < RR_PIO2_HI) term = mt.z;
+    else term = mt.z * rr_powf(rr_cosf(angle), mt.w);
+    return mt.y * 1.0f + term;
+}
+
 /* Wave state. Quirk kept on purpose: the reference never updates DirectedWave::velocity on the waves it pushes
  * (RadarCPU.cpp:285-286,364-365 copy only dir and energy out of fresnel()'s result), so every wave travels with
  * the initial 0.3 m/ns (RadarCPU.cpp:110) and only material_id tracks the medium. velocity is therefore a
@@ -205,6 +221,50 @@ __device__ __forceinline__ uint8_t rr_to_u8(float v)
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Prologue kernels: what is constant per item or per pair of media leaves the per-ray code (rr_internal.h).
+ * They call the same rr_detmath.h routines, in the same order, as the per-ray code they replace.
+ * ---------------------------------------------------------------------------------------------- */
+/* Tam = Tsm * Tas (RadarCPU.cpp:201-206; Tas.t = 0) of every (pose, azimuth) item of a launch sequence, and the map-frame
+ * origin of the item's pass-0 rays (wave origin (0,0,0), RadarCPU.cpp:108) */
+__global__ void __launch_bounds__(128) rr_prep_kernel(const RRFrameParams P)
+{
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= (uint32_t)P.n_items) return;
+    const int pose_i = (int)(item / (uint32_t)P.az_count);
+    const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
+    const rr_pose ps = P.poses[P.pose_per_azimuth ? (pose_i * RR_N_ANGLES + az) : pose_i];
+    rr_quat Rsm; Rsm.x = ps.qx; Rsm.y = ps.qy; Rsm.z = ps.qz; Rsm.w = ps.qw;
+    const float4 tq = P.tas_quat[az];
+    rr_quat Ras; Ras.x = tq.x; Ras.y = tq.y; Ras.z = tq.z; Ras.w = tq.w;
+    const rr_quat R = rr_qmul(Rsm, Ras);
+    const rr_vec3 T = rr_add(rr_qrot(Rsm, rr_v3(0.f, 0.f, 0.f)), rr_v3(ps.tx, ps.ty, ps.tz));
+    const rr_vec3 O0 = rr_add(rr_qrot(R, rr_v3(0.f, 0.f, 0.f)), T);
+    P.item_xf[3 * item + 0] = make_float4(R.x, R.y, R.z, R.w);
+    P.item_xf[3 * item + 1] = make_float4(T.x, T.y, T.z, 0.f);
+    P.item_xf[3 * item + 2] = make_float4(O0.x, O0.y, O0.z, 0.f);
+}
+
+/* media-pair constants of Snell/Fresnel (radar_algorithms.h:60-63,80-90,98,110) for every far-side medium of every
+ * material table; entry n_mat of a table = "same medium on both sides" (v2 = incidence.velocity, RadarCPU.cpp:277-280) */
+__global__ void __launch_bounds__(128) rr_mat_pairs_kernel(const float4* __restrict__ materials, int n_mat, int n_tables, RRMatPair* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tables * (n_mat + 1)) return;
+    const int t = i / (n_mat + 1), m = i - t * (n_mat + 1);
+    const double wave_v = RR_WAVE_VELOCITY;
+    const float v_t = (m < n_mat) ? materials[(size_t)t * n_mat + m].x : (float)wave_v;   /* through a float, RadarCPU.cpp:273 */
+    const double n1 = (double)v_t, n2 = wave_v;
+    RRMatPair r; r.n1 = n1; r.th_limit = 100.0; r.n12 = 0.0;
+    if (n1 > 0.0) {
+        const double n21 = n2 / n1;
+        if (fabs(n21) <= 1.0) r.th_limit = rr_asin(n21);
+        r.n12 = n1 / n2;
+    }
+    r.rs0 = (n1 - n2) / (n1 + n2);
+    out[i] = r;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Kernel 1/3: rr_trace_kernel — ONE PASS of all items: wave -> closest hit -> Snell/Fresnel + BRDF -> returns, children.
  *
  * Wavefront over the whole launch (rr_internal.h): the pass's wave list is cut into groups of 32 consecutive waves; a
@@ -268,7 +328,7 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                 item = j / S;
                 const uint32_t smp = j - item * S;
                 w.o = rr_v3(0.f, 0.f, 0.f);
-                const float* bd = P.beam_dirs + (size_t)item / (uint32_t)P.az_count * P.beam_stride;   /* per-goal bundles: rr_gen_radar_images */
+                const float* bd = P.beam_dirs + (P.beam_stride ? (size_t)(item / (uint32_t)P.az_count) * P.beam_stride : (size_t)0);   /* per-goal bundles: rr_gen_radar_images */
                 w.d = rr_v3(bd[3 * smp], bd[3 * smp + 1], bd[3 * smp + 2]);
                 w.energy = 1.0; w.time = 0.0; w.mat = 0u;
             } else {                                      /* list position j -> slot (rr_internal.h) */
@@ -284,17 +344,15 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                 item = __ldcs(ci + slot);
             }
             dbg_energy = (float)w.energy;
-            /* Tam = Tsm * Tas (RadarCPU.cpp:201-206); Tas.t = 0 */
-            const int pose_i = (int)(item / (uint32_t)P.az_count);
-            az = P.az_begin + (int)(item % (uint32_t)P.az_count);
-            const rr_pose ps = P.poses[P.pose_per_azimuth ? (pose_i * RR_N_ANGLES + az) : pose_i];
-            rr_quat Rsm; Rsm.x = ps.qx; Rsm.y = ps.qy; Rsm.z = ps.qz; Rsm.w = ps.qw;
-            const float4 tq = P.tas_quat[az];
-            rr_quat Ras; Ras.x = tq.x; Ras.y = tq.y; Ras.z = tq.z; Ras.w = tq.w;
-            const rr_quat R = rr_qmul(Rsm, Ras);
-            const rr_vec3 T = rr_add(RR_QROT(Rsm, rr_v3(0.f, 0.f, 0.f)), rr_v3(ps.tx, ps.ty, ps.tz));
+            /* Tam = Tsm * Tas of the item (rr_prep_kernel) */
+            const float4 xr = __ldg(P.item_xf + 3 * (size_t)item), xt = __ldg(P.item_xf + 3 * (size_t)item + 1);
+            rr_quat R; R.x = xr.x; R.y = xr.y; R.z = xr.z; R.w = xr.w;
+            const uint32_t pose_i = (P.material_stride | P.mat_pair_stride) ? item / (uint32_t)P.az_count : 0u;
+            if (DEBUG) az = P.az_begin + (int)(item % (uint32_t)P.az_count);
             /* ray into the map frame; closest hit within [0, 1000] m (radar_algorithms.cpp:157-158) */
-            const rr_vec3 o_m = rr_add(RR_QROT(R, w.o), T);
+            rr_vec3 o_m;
+            if (pass == 0) { const float4 x0 = __ldg(P.item_xf + 3 * (size_t)item + 2); o_m = rr_v3(x0.x, x0.y, x0.z); }
+            else o_m = rr_add(RR_QROT(R, w.o), rr_v3(xt.x, xt.y, xt.z));
             const rr_vec3 d_m = RR_QROT(R, w.d);
             const int slot_t = rr_trace<STATS>(P.nodes, P.tris, P.root_ref, go, gs, o_m, d_m, 1000.0f,
                                                range, face, stat_nodes, stat_tris);
@@ -317,39 +375,37 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                     const double wave_v = RR_WAVE_VELOCITY;
                     const double t_hit = w.time + RR_DDIV((double)range, wave_v);
 
-                    /* medium on the far side (RadarCPU.cpp:266-280) */
+                    /* medium on the far side (RadarCPU.cpp:266-280) and its Snell/Fresnel constants (rr_mat_pairs_kernel) */
                     const uint32_t air = (uint32_t)P.material_id_air;
                     const uint32_t mat_t = (w.mat == air) ? (uint32_t)P.object_materials[obj] : air;
-                    const float4 mt = P.materials[(size_t)pose_i * P.material_stride + mat_t];
-                    const float v_t = (w.mat != mat_t) ? mt.x : (float)wave_v;
+                    const double2* mpp = reinterpret_cast<const double2*>(P.mat_pairs + (size_t)pose_i * P.mat_pair_stride
+                                                                           + ((w.mat != mat_t) ? mat_t : (uint32_t)P.n_materials));
+                    const double2 mp0 = __ldg(mpp), mp1 = __ldg(mpp + 1);          /* (n1, th_limit) (n12, rs0) */
 
                     /* Snell/Fresnel (radar_algorithms.h:55-139): n1 := v2, n2 := v1 */
-                    const double n1 = (double)v_t, n2 = wave_v;
+                    const double n1 = mp0.x;
                     const float cos_i = rr_dot(rr_neg(w.d), n);
                     const float th_if = rr_acosf(cos_i);
                     const double th_i = (double)th_if;
                     const rr_vec3 d_refl = rr_add(w.d, rr_muls(rr_muls(n, 2.0f), rr_dot(rr_neg(n), w.d)));
                     rr_vec3 d_refr = rr_v3(0.f, 0.f, 0.f);
-                    rr_vec3 nn = n;
-                    if (n1 > 0.0) {
-                        const double n21 = RR_DDIV(n2, n1);
-                        double th_limit = 100.0;
-                        if (fabs(n21) <= 1.0) th_limit = rr_asin(n21);
-                        if (th_i <= th_limit) {
-                            if (rr_dot(nn, w.d) > 0.0f) nn = rr_neg(nn);
-                            if (n2 > 0.0) {
-                                const double n12 = RR_DDIV(n1, n2);
-                                const double c = rr_cos(th_i);
-                                const double k = n12 * c - sqrt(1 - n12 * n12 * (1 - c * c));
-                                d_refr = rr_add(rr_muls(w.d, (float)n12), rr_muls(nn, (float)k));
-                            }
-                        }
+                    /* refraction angle acos(refr . (-n)) (:106). Without a refracted ray (total reflection, v2 = 0) the
+                     * dot product of the zero vector is +-0 whatever n is, so the angle is the constant (float)acos(0)
+                     * (a NaN in n has already made th_i NaN and with it everything below). */
+                    double th_t = (double)RR_ACOSF_OF_ZERO;
+                    if (n1 > 0.0 && th_i <= mp0.y) {
+                        rr_vec3 nn = n;
+                        if (rr_dot(nn, w.d) > 0.0f) nn = rr_neg(nn);
+                        const double n12 = mp1.x;                                  /* n2 = 0.3 > 0 always */
+                        const double c = rr_cos(th_i);
+                        const double k = n12 * c - sqrt(1 - n12 * n12 * (1 - c * c));
+                        d_refr = rr_add(rr_muls(w.d, (float)n12), rr_muls(nn, (float)k));
+                        th_t = (double)rr_acosf(rr_dot(d_refr, rr_neg(nn)));
                     }
-                    const double th_t = (double)rr_acosf(rr_dot(d_refr, rr_neg(nn)));
                     double rs, rp;
                     const double th_sum = th_i + th_t;
                     if (th_sum < 0.0001) {
-                        rs = RR_DDIV(n1 - n2, n1 + n2); rp = rs;
+                        rs = mp1.y; rp = rs;
                     } else if (th_sum > M_PI - 0.0001) {
                         rs = 1.0; rp = 1.0;
                     } else {
@@ -368,15 +424,13 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                         keep0 = true; c_d0 = d_refl; c_e0 = e_refl; c_m0 = w.mat;
                         if (w.mat == air) {                            /* :302 — return to the sensor */
                             const float e_f = (float)e_refl;
-                            {   /* BRDF, radar_algorithms.h:168-187: (A, B, C) = (ambient, diffuse, specular) */
-                                const float lobe = rr_powf(rr_cosf(th_if), mt.w);
-                                const float total = mt.y * 1.0f + mt.z * lobe;
-                                const float ret = total * e_f;
-                                if (pass == 0 || P.record_multi_reflection) {
-                                    const float t_back = (float)(t_hit * 2.0);
-                                    sig_cell0 = rr_signal_cell((double)t_back, P.resolution);
-                                    sig_s0 = ret; sig_t0 = t_back; n_sig = 1;
-                                }
+                            const float4 mt = __ldg(P.materials + (size_t)pose_i * P.material_stride + mat_t);
+                            if (pass == 0 || P.record_multi_reflection) {
+                                /* BRDF, radar_algorithms.h:168-187: (A, B, C) = (ambient, diffuse, specular) */
+                                const float ret = rr_brdf(th_if, mt) * e_f;
+                                const float t_back = (float)(t_hit * 2.0);
+                                sig_cell0 = rr_signal_cell((double)t_back, P.resolution);
+                                sig_s0 = ret; sig_t0 = t_back; n_sig = 1;
                             }
                             if (pass > 0 && P.record_multi_path) {     /* :325-360 */
                                 const float dist_f = rr_l2norm(p_hit);
@@ -385,9 +439,7 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
                                 const double view = (double)rr_dot(w.d, to_hit);
                                 const float ang = rr_acosf(rr_dot(rr_neg(d_refl), to_hit));
                                 if (view > P.multipath_threshold) {
-                                    const float lobe = rr_powf(rr_cosf(ang), mt.w);
-                                    const float total = mt.y * 1.0f + mt.z * lobe;
-                                    const float ret = total * e_f;
+                                    const float ret = rr_brdf(ang, mt) * e_f;
                                     const double t_air = t_hit + t_sensor;
                                     const int cell = rr_signal_cell(t_air, P.resolution);
                                     if (n_sig == 0) { sig_cell0 = cell; sig_s0 = ret; sig_t0 = (float)t_air; }
@@ -720,7 +772,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     for (int k = 0; k < RR_WARPS; k++) if (s_red[k] > max_val) max_val = s_red[k];
 
     /* ================= energy_max, ambient noise, normalise, mono8 (RadarCPU.cpp:453-542) ================= */
-    const int col = (P.scroll_image + az) % RR_N_ANGLES;
+    const int col = (((P.scroll_image + az) % RR_N_ANGLES) + RR_N_ANGLES) % RR_N_ANGLES;   /* RadarCPU.cpp:457; scroll_image is validated to [0, 400] */
     const uint64_t frame_id = P.frame_id0 + (uint64_t)pose_i;
     const float signal_amp = max_val - 0.0f;
     const float noise_at_0 = (float)((double)signal_amp * P.noise_at_signal_0);
@@ -867,7 +919,7 @@ __global__ void __launch_bounds__(256) rr_gather_transpose_kernel(const uint8_t*
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {                                /* rows = cells, columns = azimuths (contiguous) */
         const int c = c0 + r, a = a0 + tx;
-        if (c < C && a < RR_N_ANGLES) o[(size_t)c * RR_N_ANGLES + (scroll + a) % RR_N_ANGLES] = tile[tx][r];
+        if (c < C && a < RR_N_ANGLES) o[(size_t)c * RR_N_ANGLES + (((scroll + a) % RR_N_ANGLES) + RR_N_ANGLES) % RR_N_ANGLES] = tile[tx][r];
     }
 }
 
@@ -907,6 +959,20 @@ extern "C" cudaError_t rr_launch_trace(const RRFrameParams* P, int pass, int gri
     if (debug) rr_trace_kernel<true, true><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
     else if (stats) rr_trace_kernel<true, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
     else rr_trace_kernel<false, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t rr_launch_prep(const RRFrameParams* P, cudaStream_t st)
+{
+    rr_prep_kernel<<<(unsigned)((P->n_items + 127) / 128), 128, 0, st>>>(*P);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t rr_launch_mat_pairs(const float4* materials, int n_mat, int n_tables, RRMatPair* out, cudaStream_t st)
+{
+    const int n = n_tables * (n_mat + 1);
+    if (n <= 0) return cudaSuccess;
+    rr_mat_pairs_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(materials, n_mat, n_tables, out);
     return cudaGetLastError();
 }
 

@@ -26,6 +26,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <new>
+#include <stdexcept>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -163,6 +165,10 @@ bool load_ply(const std::string& path, Soup& s, std::string& err)
         if (is_vertex && (ix < 0 || iy < 0 || iz < 0)) { err = "PLY: vertex element without x/y/z"; return false; }
         if (is_face && il < 0) { err = "PLY: face element without vertex_indices"; return false; }
         if (is_face && !have_vertex) { err = "PLY: face element before vertex element"; return false; }
+        /* an element can not hold more records than the rest of the file has bytes (ascii: >= 2 bytes per record,
+         * binary: >= 1): bound the count BEFORE sizing anything by it */
+        const size_t bytes_left = (fmt == 0) ? data.size() - pos : (size_t)(bend - bp);
+        if (e.count > bytes_left) { err = "PLY: element '" + e.name + "' declares more records than the file holds"; return false; }
         if (is_vertex) { s.v.resize(e.count * 3); n_verts = e.count; have_vertex = true; }
         for (size_t r = 0; r < e.count && ok; r++) {
             for (size_t k = 0; k < e.props.size() && ok; k++) {
@@ -535,7 +541,7 @@ void set_err(char* err, size_t cap, const std::string& msg)
 
 extern "C" {
 
-int rr_mesh_load(const char* path, rr_mesh* out, char* err, size_t err_cap)
+int rr_mesh_load(const char* path, rr_mesh* out, char* err, size_t err_cap) try
 {
     if (!path || !out) { set_err(err, err_cap, "rr_mesh_load: NULL argument"); return RR_ERR_INVALID_ARGUMENT; }
     memset(out, 0, sizeof(*out));
@@ -555,13 +561,17 @@ int rr_mesh_load(const char* path, rr_mesh* out, char* err, size_t err_cap)
     if (!out->verts_xyz || !out->tri_idx || !out->tri_object_id) {
         rr_mesh_free(out);
         set_err(err, err_cap, "rr_mesh_load: out of memory");
-        return RR_ERR_INVALID_ARGUMENT;
+        return RR_ERR_OUT_OF_MEMORY;
     }
     memcpy(out->verts_xyz, s.v.data(), s.v.size() * sizeof(float));
     memcpy(out->tri_idx, s.t.data(), s.t.size() * sizeof(uint32_t));
     memcpy(out->tri_object_id, s.o.data(), s.o.size() * sizeof(uint32_t));
     return RR_OK;
 }
+catch (const std::bad_alloc&) { if (out) rr_mesh_free(out); set_err(err, err_cap, "rr_mesh_load: out of memory"); return RR_ERR_OUT_OF_MEMORY; }
+catch (const std::length_error&) { if (out) rr_mesh_free(out); set_err(err, err_cap, "rr_mesh_load: a size declared in the file is absurd"); return RR_ERR_OUT_OF_MEMORY; }
+catch (const std::exception& ex) { if (out) rr_mesh_free(out); set_err(err, err_cap, std::string("rr_mesh_load: ") + ex.what()); return RR_ERR_INVALID_ARGUMENT; }
+catch (...) { if (out) rr_mesh_free(out); set_err(err, err_cap, "rr_mesh_load: unknown exception"); return RR_ERR_INVALID_ARGUMENT; }
 
 void rr_mesh_free(rr_mesh* m)
 {

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libradarays_b200.so does not export %s" % n
     assert sorted(capi.SYMBOLS) == names
-    assert L.rr_abi_version() == capi.ABI_VERSION == 2
+    assert L.rr_abi_version() == capi.ABI_VERSION == 3
 
 
 def test_config_defaults_match_reference_cfg():

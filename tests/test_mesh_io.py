@@ -183,3 +183,21 @@ def test_dae_errors(tmp_path):
     notdae.write_text("<html></html>")
     with pytest.raises(RadaRaysError):
         load_mesh(notdae)
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian"])
+def test_absurd_element_counts_return_a_status_instead_of_aborting(tmp_path, fmt):
+    """A header that declares more records than the file can hold must come back as an rr_status through the C ABI
+    (it used to throw std::length_error across extern "C" and abort the host process)."""
+    p = tmp_path / "bomb.ply"
+    p.write_bytes(("ply\nformat %s 1.0\nelement vertex 999999999999999999\nproperty float x\nproperty float y\n"
+                   "property float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n" % fmt).encode()
+                  + b"0 0 0\n")
+    with pytest.raises(RadaRaysError) as e:
+        load_mesh(p)
+    assert e.value.code in (-1, -7)
+    p.write_bytes(("ply\nformat %s 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                   "element face 18446744073709551615\nproperty list uchar int vertex_indices\nend_header\n" % fmt).encode()
+                  + b"\0" * 64)
+    with pytest.raises(RadaRaysError):
+        load_mesh(p)
