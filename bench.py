@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py — polar frames/s of the RadaRays hot path on B200 (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference-semantics CPU path on the host cores
+  python bench.py --gpus N --steps K --warmup W                      # this repo's CUDA path, BASELINE config 2
+  python bench.py --config {2,3,4,5} [--shard pose|azimuth] [--exchange p2p|nccl] [--samples S]
+  python bench.py --impl reference ...                               # the reference's CPU sources on the host cores
 
-Workload (BASELINE.json configs[1]): synthetic MulRan-KAIST-scale urban mesh (>= 5 M triangles), 400 azimuths x
-3360 range bins, 3 passes, 256 beam samples per azimuth, per-face materials, MulRan dyn-reconfigure values
-(cfg/mulran_kaist_dyncfg.yaml), Perlin ambient noise. One STEP = one call of the frame kernel over a batch of
-16 street-level poses (16 polar frames). `value` = frames/s with poses and images resident in HBM;
-`e2e` = the same through rr_simulate() with HOST buffers (pinned H2D of the poses, D2H of the mono8 images).
-N > 1: one process per GPU, mesh/BVH replicated, poses sharded (weak scaling), no data-path collective.
+BASELINE.json configs (numbered as SURVEY.md §8d):
+  2  urban-5M (>= 5 M triangles), 400 az x 3360 bins, 3 passes, 256 samples/az, MulRan dyn-cfg, Perlin noise.
+     STEP = one 16-pose call per GPU; N > 1: poses sharded, BVH replicated, no data-path collective ("weak").
+  3  as 2 with 2 passes and --samples S in {64 ... 2048} (default 2048): the beam-sampling sweep end the roofline is quoted on.
+  4  warehouse-1M, 5 passes, 256 samples, dielectric/metal mix. Default --shard azimuth: every frame is cut into N column
+     shards, rr_simulate_sharded exchanges the finished columns through NVLink peer memory from inside the draw kernel
+     (--exchange nccl: column shards + all_gather instead); STEP = the same 16 frames on every GPU count ("strong").
+  5  urban-5M, 10 000 poses of the seeded street trajectory, pose-sharded; STEP = the whole trajectory ("strong").
+`value` = frames/s with poses and images resident in HBM; `e2e` = the same through the host-buffer API (rr_simulate /
+H2D poses + rr_simulate_sharded + D2H images) with the copies inside the timed region.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -26,42 +32,76 @@ sys.path.insert(0, ROOT)
 
 from radarays_ros_b200 import MULRAN_DYNCFG, N_ANGLES, Pose, RadarModelConfig, scenes  # noqa: E402
 
-POSES_PER_STEP = 16
-N_SAMPLES = 256
-N_PASSES = 3
 N_CELLS = 3360
+TRAJ_POSES = 10000
 
 
-def workload_cfg():
-    return RadarModelConfig(**dict(MULRAN_DYNCFG, n_cells=N_CELLS, n_samples=N_SAMPLES, n_reflections=N_PASSES,
-                                   include_motion=0))
+class Workload:
+    """One BASELINE.json config: scene, parameters, the poses of a step."""
 
+    def __init__(self, config, small, samples=None, traj=None):
+        self.config, self.small = config, small
+        over = dict(n_cells=N_CELLS, include_motion=0)
+        if config in (2, 5):
+            over.update(n_samples=256, n_reflections=3)
+        elif config == 3:
+            over.update(n_samples=samples or 2048, n_reflections=2)
+        elif config == 4:
+            over.update(n_samples=256, n_reflections=5, resolution=0.02)
+        else:
+            raise ValueError("config must be 2, 3, 4 or 5")
+        if samples and config != 3:
+            over.update(n_samples=samples)
+        self.cfg = RadarModelConfig(**dict(MULRAN_DYNCFG, **over))
+        self.max_waves = 256 * 10 if config == 4 else 0
+        self.scene_name = ("warehouse" if config == 4 else "urban") + ("_small" if small else ("" if config == 4 else "_5m"))
+        self.n_traj = traj or (400 if small else TRAJ_POSES)
+        self.poses_per_step = self.n_traj if config == 5 else 16
+        self.default_shard = "azimuth" if config == 4 else "pose"
 
-def make_scene(small):
-    return scenes.urban_small() if small else scenes.urban_5m()
+    def make_scene(self):
+        return getattr(scenes, self.scene_name)()
 
+    def describe(self, scene):
+        c = self.cfg
+        mesh = {"urban_5m": "urban-5M synthetic MulRan-KAIST-scale mesh", "urban_small": "urban-small debug mesh",
+                "warehouse": "warehouse-1M ORU-style indoor mesh", "warehouse_small": "warehouse-small debug mesh"}[self.scene_name]
+        poses = "%d trajectory poses per step" % self.n_traj if self.config == 5 else "16 poses per step"
+        return "BASELINE config %d: %s, 400 az x %d bins, %d passes, %d samples/az, %s" % (
+            self.config, mesh, c.n_cells, c.n_reflections, c.n_samples, poses)
 
-def rank_poses(scene, rank, small):
-    """16 fixed street-level poses for rank 0; other ranks get their own 16 from the
-    seeded street trajectory (config 5, pose-sharded)."""
-    if rank == 0:
-        ps = [scene.poses[i % len(scene.poses)] for i in range(POSES_PER_STEP)]
-    else:
-        ext = 400.0 if small else 2000.0
+    def step_poses(self, scene, rank, world, shard):
+        """(x, y, z, yaw) tuples this rank renders in one step."""
+        if self.config == 5:
+            ext = 400.0 if self.small else 2000.0
+            traj = scenes.trajectory(scene, self.n_traj, extent=ext)
+            if self.small:
+                traj = [(x * 0.2, y * 0.2, z, yaw) for (x, y, z, yaw) in traj]
+            return traj[rank::world]
+        base = [scene.poses[i % len(scene.poses)] for i in range(16)]
+        if shard == "azimuth" or rank == 0:
+            return base                                     # azimuth shards: every rank works on the SAME 16 frames
+        # pose-sharded weak scaling: other ranks get their own 16 poses
+        if self.config == 4:
+            return [scene.poses[(i + 5 * rank) % len(scene.poses)] for i in range(16)]
+        ext = 400.0 if self.small else 2000.0
         traj = scenes.trajectory(scene, 10000, extent=ext)
-        ps = [traj[(rank * 997 + i * 61) % len(traj)] for i in range(POSES_PER_STEP)]
-        if small:
+        ps = [traj[(rank * 997 + i * 61) % len(traj)] for i in range(16)]
+        if self.small:
             ps = [(x * 0.2, y * 0.2, z, yaw) for (x, y, z, yaw) in ps]
-    arr = (Pose * POSES_PER_STEP)()
+        return ps
+
+
+def pose_array(ps):
+    arr = (Pose * len(ps))()
     for i, p in enumerate(ps):
         arr[i] = Pose.from_xyz_yaw(*p)
     return arr
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe). The timed region lasts tens of
-    milliseconds, so the sampler reads NVML in-process every 2 ms (nvidia_ml_py); nvidia-smi, one process per sample,
-    is the fallback."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML in-process every 2 ms
+    (nvidia_ml_py); nvidia-smi, one process per sample, is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -77,7 +117,6 @@ class ClockSampler(threading.Thread):
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists plain indices
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
             phys = gpu_index
             if vis and all(x.strip().isdigit() for x in vis.split(",")):
@@ -114,7 +153,7 @@ class ClockSampler(threading.Thread):
                 else:
                     self._sample_smi()
             except Exception:
-                if self._h is not None:        # NVML hiccup: fall back for the rest of the run
+                if self._h is not None:
                     self._h = None
                     self.source = "nvidia-smi"
             self.stop_flag.wait(0.002 if self._h is not None else 0.2)
@@ -138,12 +177,41 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+KERNEL_SOURCES = ["radarays_ros_b200/csrc/rr_kernels.cu", "radarays_ros_b200/csrc/rr_internal.h",
+                  "radarays_ros_b200/csrc/rr_detmath.h"]
+
+
+def kernel_source_hash():
+    """sha256 over the kernel sources: the ncu-derived numbers in profiles/roofline_traffic.json are stamped with it and
+    are only quoted when they were captured from THIS kernel version."""
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_evidence(config, n_samples):
+    """DRAM traffic / hit rates / issue utilisation of rr_trace_kernel from the committed ncu launch list of this
+    workload (profiles/roofline_traffic.json, tools/profile_configs.sh). None when absent or stale."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None, "profiles/roofline_traffic.json missing"
+    if d.get("kernel_source_hash") != kernel_source_hash():
+        return None, "profiles/roofline_traffic.json was captured from another kernel version (hash %s != %s)" % (
+            d.get("kernel_source_hash"), kernel_source_hash())
+    e = d.get("workloads", {}).get("config%d_s%d" % (config, n_samples))
+    return e, ("profiles/roofline_traffic.json" if e else "no ncu capture for this workload")
+
+
 _CPU_SCENE = {}
 
 
 def cpu_scene(scene):
-    """Reference-semantics CPU path, built once: oracle/_ref (the reference's OWN sources compiled against shims) when it
-    is present, else the oracle port. Returns (object with .simulate, kind)."""
+    """Reference CPU path, built once: oracle/_ref (the reference's OWN RadarCPU.cpp / Radar.cpp / radar_algorithms.cpp
+    compiled against shim headers; its ray caster is a scalar BVH walk, NOT Embree) when present, else the oracle port."""
     if "obj" not in _CPU_SCENE:
         ref_so = os.path.join(ROOT, "oracle", "_ref", "libradarays_ref.so")
         obj, kind = None, "port"
@@ -151,7 +219,7 @@ def cpu_scene(scene):
             try:
                 from oracle import ref as oref
                 obj, kind = oref.RefScene(scene), "reference"
-            except Exception as e:  # fall back to the port, say so
+            except Exception as e:
                 print("bench: oracle/_ref unusable (%s), using the oracle port" % e, file=sys.stderr)
         if obj is None:
             from oracle import oracle
@@ -160,9 +228,14 @@ def cpu_scene(scene):
     return _CPU_SCENE["obj"], _CPU_SCENE["kind"]
 
 
+CPU_DETAIL = {"reference": "the reference's own RadarCPU.cpp/Radar.cpp/radar_algorithms.cpp, -O3 x86-64-v3, OpenMP over azimuths "
+                           "(RadarCPU.cpp:155), compiled against shim headers whose ray caster is a scalar BVH walk — NOT Embree",
+              "port": "oracle/rr_oracle.cpp (CPU restatement), OpenMP over azimuths"}
+
+
 def cpu_reference_run(scene, cfg, dirs, poses, n_frames, noise_seed):
-    """n_frames frames on all host cores, OpenMP over azimuths like RadarCPU.cpp:155; timed by the CPU path's own
-    stopwatch around the azimuth loop (RadarCPU.cpp:147-148,550) — BVH build excluded."""
+    """n_frames frames on all host cores; timed by the CPU path's own stopwatch around the azimuth loop
+    (RadarCPU.cpp:147-148,550) — BVH build excluded."""
     cores = os.cpu_count() or 1
     obj, kind = cpu_scene(scene)
     t = 0.0
@@ -175,20 +248,31 @@ def cpu_reference_run(scene, cfg, dirs, poses, n_frames, noise_seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: enough for a >= 0.5 s timed region)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--small", action="store_true", help="debug: ~60k-triangle mesh instead of urban-5M")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--shard", default=None, choices=["pose", "azimuth"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="azimuth shards: NVLink peer stores fused into the draw kernel | NCCL all_gather")
+    ap.add_argument("--samples", type=int, default=None, help="beam samples per azimuth (config 3 sweep: 64 ... 2048)")
+    ap.add_argument("--traj", type=int, default=None, help="config 5: trajectory length (default 10000)")
+    ap.add_argument("--chunk", type=int, default=256, help="config 5: poses per call")
+    ap.add_argument("--small", action="store_true", help="debug: small meshes instead of urban-5M / warehouse-1M")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample (~10 s of host work)")
     ap.add_argument("--lanes", type=int, default=2, help="internal streams per call (rr_set_lanes); 1 = serial launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    K, W = args.steps, max(args.warmup, 0)
-    cfg = workload_cfg()
-    workload = ("urban-small debug mesh" if args.small else "urban-5M synthetic MulRan-KAIST-scale mesh") + \
-        ", 400 az x %d bins, %d passes, %d samples/az, 16 poses per step" % (N_CELLS, N_PASSES, N_SAMPLES)
+    wl = Workload(args.config, args.small, args.samples, args.traj)
+    shard = args.shard or wl.default_shard
+    cfg = wl.cfg
+    PPS = wl.poses_per_step
+    W = max(args.warmup, 0)
+    if args.steps is not None:
+        K = args.steps
+    else:
+        K = {2: 250, 3: 60, 4: 150, 5: 3}[args.config] if args.impl == "b200" else 10
     noise_seed, beam_seed = 20240310, 20240310
 
     # ------------------------------------------------------------------------------------------ reference arm
@@ -196,25 +280,27 @@ def main():
         if rank != 0:
             return 0
         from oracle import oracle
-        scene = make_scene(args.small)
+        scene = wl.make_scene()
         model = cfg.derive_model()
         dirs = oracle.sample_cone(model.beam_width, model.n_samples, cfg.beam_sample_dist,
                                   cfg.beam_sample_dist_normal_p_in_cone, beam_seed)
-        poses = rank_poses(scene, 0, args.small)
+        ps = wl.step_poses(scene, 0, 1, shard)
+        poses = pose_array(ps[:16])
         cores = os.cpu_count() or 1
         for _ in range(min(W, 1)):
             cpu_reference_run(scene, cfg, dirs, poses, 1, noise_seed)
         t_tot, n_tot, kind = 0.0, 0, "port"
         for s in range(K):
-            fps, kind, cores, t = cpu_reference_run(scene, cfg, dirs, [poses[s % POSES_PER_STEP]], 1, noise_seed)
+            fps, kind, cores, t = cpu_reference_run(scene, cfg, dirs, [poses[s % len(poses)]], 1, noise_seed)
             t_tot += t
             n_tot += 1
         val = n_tot / t_tot
         line = {"impl": "reference", "metric": "polar frames/s", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": K, "warmup": W, "ms_per_step": 1000.0 * t_tot / max(K, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-                "config": {"workload": workload, "cpu_sample": "1 frame (400 az x %d samples x %d passes) per step" % (N_SAMPLES, N_PASSES)},
-                "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind,
+                "config": {"workload": wl.describe(scene), "cpu_sample": "1 frame (400 az x %d samples x %d passes) per step" % (
+                    cfg.n_samples, cfg.n_reflections)},
+                "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind, "kind_detail": CPU_DETAIL[kind],
                                  "sample": "%d steps x 1 frame of the same workload, OpenMP over azimuths" % K},
                 "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -226,6 +312,7 @@ def main():
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device; the B200 arm has no CPU fallback", file=sys.stderr)
         return 2
+    from radarays_ros_b200.distributed import ShardedRadar, azimuth_shard
     from radarays_ros_b200.radar import RadarB200
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -233,33 +320,64 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     t0 = time.time()
-    scene = make_scene(args.small)
+    scene = wl.make_scene()
     t_scene = time.time() - t0
     radar = RadarB200(scene, cfg, device=local_rank, beam_seed=beam_seed, noise_seed=noise_seed)
+    if wl.max_waves:
+        radar.setMaxWavesPerAzimuth(wl.max_waves)
     radar.setLanes(args.lanes)
     dirs = radar.getBeamSamples()
-    poses = rank_poses(scene, rank, args.small)
-    poses_np = np.frombuffer(poses, dtype=np.float32).reshape(POSES_PER_STEP, 7).copy()
+    ps = wl.step_poses(scene, rank, world, shard)
+    n_mine = len(ps)                                       # poses this rank touches per step
+    poses = pose_array(ps)
+    poses_np = np.frombuffer(poses, dtype=np.float32).reshape(n_mine, 7).copy()
     d_poses = torch.from_numpy(poses_np).to(dev)
-    d_out = torch.zeros((POSES_PER_STEP, N_CELLS, N_ANGLES), dtype=torch.uint8, device=dev)
+    chunk = min(args.chunk, n_mine) if args.config == 5 else n_mine
+    d_out = torch.zeros((chunk, N_CELLS, N_ANGLES), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
     stream = torch.cuda.Stream(device=dev)
+    sharded = None
+    if shard == "azimuth":
+        sharded = ShardedRadar(radar, rank, world, p2p=(args.exchange == "p2p"), max_poses=chunk)
 
     def step(frame0):
-        radar.simulate_device(d_poses.data_ptr(), POSES_PER_STEP, d_out.data_ptr(), frame_id=frame0,
-                              stream=stream.cuda_stream)
+        """one step of this rank on `stream` (device-resident poses and images)"""
+        for c0 in range(0, n_mine, chunk):
+            n = min(chunk, n_mine - c0)
+            src = d_poses.data_ptr() + c0 * 28
+            if sharded is None:
+                radar.simulate_device(src, n, d_out.data_ptr(), frame_id=frame0 + c0, stream=stream.cuda_stream)
+            elif args.exchange == "p2p":
+                radar.simulate_sharded(src, n, d_out.data_ptr(), frame_id=frame0 + c0, stream=stream.cuda_stream)
+            else:
+                sharded.simulate_batch_nccl(d_poses[c0:c0 + n], d_out[:n], frame_id=frame0 + c0, stream=stream)
 
-    # algorithmic bytes of one launch: counted by the stats build of the same kernel (deterministic)
+    # algorithmic bytes of one step of THIS rank: one untimed step with the counting instantiation of the same kernels
+    # (counters are per call, so the step is walked call by call)
+    radar.setStatsMode(True)
     nodes = tris = hits = casts = 0
-    for i in range(POSES_PER_STEP):
-        _, st = radar.simulate_stats(poses[i], frame_id=i)
+    bvh_bytes = bvh_build_ms = 0
+    for c0 in range(0, n_mine, chunk):
+        n = min(chunk, n_mine - c0)
+        src = d_poses.data_ptr() + c0 * 28
+        with torch.cuda.stream(stream):
+            if sharded is None:
+                radar.simulate_device(src, n, d_out.data_ptr(), frame_id=c0, stream=stream.cuda_stream)
+            elif args.exchange == "p2p":
+                radar.simulate_sharded(src, n, d_out.data_ptr(), frame_id=c0, stream=stream.cuda_stream)
+            else:
+                sharded.simulate_batch_nccl(d_poses[c0:c0 + n], d_out[:n], frame_id=c0, stream=stream)
+        torch.cuda.synchronize()
+        st = radar.get_stats()
         nodes += st.nodes_visited; tris += st.tris_tested; hits += st.n_hits; casts += st.n_casts
-    bvh_stats = radar.get_stats()
-    alg_bytes = 32 * nodes + 48 * tris + 4 * hits + POSES_PER_STEP * N_ANGLES * N_CELLS
+    radar.setStatsMode(False)
+    cols_mine = azimuth_shard(rank, world)[1] if sharded is not None else N_ANGLES
+    img_bytes_step = n_mine * cols_mine * N_CELLS
+    alg_bytes = 32 * nodes + 48 * tris + 4 * hits + img_bytes_step
 
     with torch.cuda.stream(stream):
         for w in range(W):
-            step(w * POSES_PER_STEP)
+            step(w * PPS)
     torch.cuda.synchronize()
     radar.kernel_times()                                   # reset the per-kernel event ring
     sampler = ClockSampler(local_rank)
@@ -274,7 +392,7 @@ def main():
         for s in range(K):
             flush.fill_(s & 0xff)                       # L2 flush between timed iterations (outside the event pair)
             evs[s][0].record(stream)
-            step((W + s) * POSES_PER_STEP)
+            step((W + s) * PPS)
             evs[s][1].record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -285,93 +403,202 @@ def main():
     total_ms = float(sum(step_ms))
     img_sum = int(d_out.sum().item())
 
-    # roofline leg: the same K steps with strictly serial launches (one lane), so that the CUDA events the library
-    # records on the launch stream around its kernels time each kernel ALONE (in the timed region above two
-    # sub-batches of a step overlap on two streams, which is what `value` measures)
+    # roofline leg: the same steps with strictly serial launches (one lane), so that the CUDA events the library records
+    # on the launch stream around its kernels time each kernel ALONE (in the timed region above two sub-batches of a step
+    # overlap on two streams, which is what `value` measures)
+    KR = min(K, 200 if args.config != 5 else 1)
     radar.kernel_times()
     radar.setLanes(1)
     with torch.cuda.stream(stream):
         step(0)
         torch.cuda.synchronize()
         radar.kernel_times()
-        for s in range(K):
+        for s in range(KR):
             flush.fill_(s & 0xff)
-            step((W + s) * POSES_PER_STEP)
+            step((W + s) * PPS)
     torch.cuda.synchronize()
     trace_ms_sum, draw_ms_sum, n_pairs = radar.kernel_times()     # events around the kernels, on the launch stream
+    seq_per_step = max(1, n_pairs // max(KR, 1)) if args.config == 5 else 1
     radar.setLanes(args.lanes)
 
-    # end-to-end through the public host-buffer API (pinned H2D poses, D2H images inside the timed region)
-    # caller-owned page-locked result buffer, as a ROS node would keep for its sensor_msgs::Image payloads
-    out_pinned = torch.empty((POSES_PER_STEP, N_CELLS, N_ANGLES), dtype=torch.uint8, pin_memory=True)
+    # single-frame latency of the sharded plane (one pose, all ranks), device time
+    single_ms = None
+    if sharded is not None:
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                radar.simulate_sharded(d_poses.data_ptr(), 1, d_out.data_ptr(), frame_id=7, stream=stream.cuda_stream) \
+                    if args.exchange == "p2p" else sharded.simulate_batch_nccl(d_poses[:1], d_out[:1], frame_id=7, stream=stream)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for i in range(50):
+                radar.simulate_sharded(d_poses.data_ptr() + (i % n_mine) * 28, 1, d_out.data_ptr(), frame_id=100 + i, stream=stream.cuda_stream) \
+                    if args.exchange == "p2p" else sharded.simulate_batch_nccl(d_poses[i % n_mine:i % n_mine + 1], d_out[:1], frame_id=100 + i, stream=stream)
+            b.record(stream)
+        torch.cuda.synchronize()
+        single_ms = a.elapsed_time(b) / 50
+
+    # ---- end to end through the public host-buffer API, copies inside the timed region ----
+    # (a) caller-owned page-locked result buffer (what the RadarB200 adapter keeps registered for its sensor_msgs::Image
+    #     payloads), (b) a plain pageable numpy buffer (a caller that does not pin): both reported.
+    KE = K if args.config != 5 else min(K, 2)
+    out_pinned = torch.empty((chunk, N_CELLS, N_ANGLES), dtype=torch.uint8, pin_memory=True)
     out_np = out_pinned.numpy()
-    out_host = None
-    for w in range(min(W, 2)):
-        out_host = radar.simulate(poses, frame_id=0, out=out_np)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0 = time.perf_counter()
-    for s in range(K):
-        out_host = radar.simulate(poses, frame_id=(W + s) * POSES_PER_STEP, out=out_np)
-    e2e_s = time.perf_counter() - e0
+    h_poses = torch.from_numpy(poses_np).pin_memory()
+
+    def e2e_step(frame0, out):
+        for c0 in range(0, n_mine, chunk):
+            n = min(chunk, n_mine - c0)
+            if sharded is None:
+                radar.simulate(poses[c0:c0 + n] if args.config == 5 else poses, frame_id=frame0 + c0, out=out[:n])
+            else:
+                # host poses -> device, sharded render + exchange, full images -> host on the consuming rank (0)
+                with torch.cuda.stream(stream):
+                    d_poses[c0:c0 + n].copy_(h_poses[c0:c0 + n], non_blocking=True)
+                    if args.exchange == "p2p":
+                        radar.simulate_sharded(d_poses.data_ptr() + c0 * 28, n, d_out.data_ptr(), frame_id=frame0 + c0, stream=stream.cuda_stream)
+                    else:
+                        sharded.simulate_batch_nccl(d_poses[c0:c0 + n], d_out[:n], frame_id=frame0 + c0, stream=stream)
+                    if rank == 0:
+                        out_pinned[:n].copy_(d_out[:n], non_blocking=True)
+                stream.synchronize()
+
+    def e2e_leg(out):
+        for w in range(min(W, 2)):
+            e2e_step(0, out)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = time.perf_counter()
+        for s in range(KE):
+            e2e_step((W + s) * PPS, out)
+        torch.cuda.synchronize()
+        return time.perf_counter() - e0
+
+    e2e_s = e2e_leg(out_np)
+    e2e_pageable_s = None
+    if sharded is None and args.config != 5:
+        e2e_pageable_s = e2e_leg(np.empty((chunk, N_CELLS, N_ANGLES), np.uint8))
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     clocks = sampler.summary()
 
-    t_red = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    # the default N > 1 run (pose-sharded) also exercises the azimuth-sharded exchange once, so that the driver's scaling
+    # run carries evidence of the fused draw + NVLink peer-store path at every N
+    az_leg = None
+    if world > 1 and sharded is None and args.config in (2, 4):
+        try:
+            sh = ShardedRadar(radar, rank, world, p2p=True, max_poses=16)
+            base = pose_array(wl.step_poses(scene, 0, 1, "azimuth"))
+            d_b = torch.from_numpy(np.frombuffer(base, dtype=np.float32).reshape(16, 7).copy()).to(dev)
+            d_full = torch.zeros((16, N_CELLS, N_ANGLES), dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    radar.simulate_sharded(d_b.data_ptr(), 16, d_full.data_ptr(), frame_id=0, stream=stream.cuda_stream)
+                torch.cuda.synchronize(); dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for i in range(20):
+                    radar.simulate_sharded(d_b.data_ptr(), 16, d_full.data_ptr(), frame_id=0, stream=stream.cuda_stream)
+                b.record(stream)
+            torch.cuda.synchronize()
+            radar.get_stats()
+            t_az = torch.tensor([a.elapsed_time(b) / 20], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_az, op=dist.ReduceOp.MAX)
+            chk = torch.tensor([int(d_full.sum().item())], dtype=torch.int64, device=dev)
+            allchk = [torch.zeros_like(chk) for _ in range(world)]
+            dist.all_gather(allchk, chk)
+            az_leg = {"what": "the SAME 16 frames azimuth-sharded over %d GPUs, columns exchanged by NVLink peer stores from the draw kernel (rr_simulate_sharded)" % world,
+                      "ms_per_16_frames": float(t_az.item()), "frames_per_s": 16e3 / float(t_az.item()),
+                      "all_ranks_identical": all(int(c.item()) == int(chk.item()) for c in allchk),
+                      "image_checksum": int(chk.item())}
+        except Exception as e:  # evidence leg only: never fail the bench line
+            az_leg = {"error": str(e)[:200]}
+
+    t_red = torch.tensor([total_ms, e2e_s * 1000.0, (e2e_pageable_s or 0.0) * 1000.0, single_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_red, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = float(t_red[0].item()), float(t_red[1].item())
-    frames = world * POSES_PER_STEP * K
-    value = frames / (total_ms_max / 1000.0)
-    e2e_value = frames / (e2e_ms_max / 1000.0)
+    total_ms_max, e2e_ms_max, e2e_pg_ms_max, single_ms_max = [float(x) for x in t_red.tolist()]
+    # frames of the whole job per step: azimuth shards work on the same frames, pose shards on different ones
+    if args.config == 5:
+        frames_step = wl.n_traj
+    elif sharded is not None:
+        frames_step = PPS
+    else:
+        frames_step = world * PPS
+    value = frames_step * K / (total_ms_max / 1000.0)
+    e2e_value = frames_step * KE / (e2e_ms_max / 1000.0)
+    casts_t = torch.tensor([casts], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(casts_t, op=dist.ReduceOp.SUM)
+    casts_all = float(casts_t.item())
 
     if rank == 0:
         peak, peak_src = peak_hbm()
-        # dominant kernel = rr_trace_kernel: its algorithmic gather bytes over ITS average launch duration
-        trace_bytes = 32 * nodes + 48 * tris + 4 * hits
-        avg_launch_s = (trace_ms_sum / max(n_pairs, 1)) / 1000.0
+        # dominant kernel = rr_trace_kernel: its algorithmic gather bytes over ITS average duration per launch sequence
+        trace_bytes = (32 * nodes + 48 * tris + 4 * hits) / seq_per_step
+        n_seq = max(n_pairs, 1)
+        avg_launch_s = (trace_ms_sum / n_seq) / 1000.0
         achieved = trace_bytes / avg_launch_s / 1e9
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tr_path) and not args.small:
-            try:
-                traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        ev, ev_src = ncu_evidence(args.config, cfg.n_samples) if not args.small else (None, "debug mesh")
+        traffic = ev.get("dram_bytes_per_launch") if ev else None
         cpu_fps, cpu_kind, cpu_cores, cpu_t = (None, "port", os.cpu_count() or 1, 0.0)
         if args.cpu_frames > 0 and world == 1:          # the CPU baseline is timed at N = 1 only (host cores shared by the ranks otherwise)
-            cpu_fps, cpu_kind, cpu_cores, cpu_t = cpu_reference_run(scene, cfg, dirs, poses, args.cpu_frames, noise_seed)
+            cpu_fps, cpu_kind, cpu_cores, cpu_t = cpu_reference_run(scene, cfg, dirs, pose_array(ps[:16]), args.cpu_frames, noise_seed)
+        if sharded is not None:
+            par = "azimuth-sharded x%d (%s), BVH replicated" % (world, "NVLink peer stores fused into rr_draw_kernel" if args.exchange == "p2p" else "NCCL all_gather of column shards")
+        else:
+            par = "pose-sharded x%d, BVH replicated, no data-path collective" % world
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                # what actually binds the kernel (ncu, profiles/): the gathers are served by L1/L2, the SMs are busy issuing
+                "binding": "instruction issue + warp divergence (the algorithmic gather is L1/L2-served; see dram_frac)",
+                "dram_gbs": (traffic / avg_launch_s / 1e9) if traffic else None,
+                "dram_frac": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
+                "issue_active_pct": ev.get("issue_active_pct") if ev else None,
+                "threads_per_inst": ev.get("threads_per_inst") if ev else None,
+                "l1_hit_pct": ev.get("l1_hit_pct") if ev else None, "l2_hit_pct": ev.get("l2_hit_pct") if ev else None,
+                "ncu_source": ev_src, "kernel_source_hash": kernel_source_hash(),
+                "kernel": "rr_trace_kernel", "kernel_ms": trace_ms_sum / n_seq,
+                "kernel_share_of_step": trace_ms_sum / max(trace_ms_sum + draw_ms_sum, 1e-9),
+                "algorithmic_bytes_per_launch": trace_bytes,
+                "formula": "32 B x nodes_visited + 48 B x tris_tested + 4 B x hits per launch sequence = the %d per-pass launches of rr_trace_kernel over rank 0's poses (32-byte binary BVH node, 48-byte triangle; counted by the counting instantiation of the same kernel; kernel_ms = their summed duration incl. the %d rr_scan_kernel launches between them, CUDA events on the launch stream, one lane)" % (cfg.n_reflections, cfg.n_reflections - 1),
+                "draw_kernel_ms": draw_ms_sum / n_seq, "step_algorithmic_bytes": alg_bytes,
+                "step_achieved_gbs": alg_bytes / ((total_ms / K) / 1000.0) / 1e9,
+                "nodes_visited": nodes, "tris_tested": tris, "nodes_per_cast": nodes / max(casts, 1), "tris_per_cast": tris / max(casts, 1)}
+        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_mine * 28,
+               "d2h_bytes_per_step": (PPS if sharded is not None else n_mine) * N_CELLS * N_ANGLES,
+               "result_buffer": "page-locked caller buffer", "steps": KE}
+        if e2e_pageable_s is not None:
+            e2e["pageable_value"] = frames_step * KE / (e2e_pg_ms_max / 1000.0)
+            e2e["pageable_note"] = "same call with a plain pageable result buffer (library stages through its own pinned buffer + threaded memcpy)"
         line = {
             "metric": "polar frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True,
+            "scaling": "strong" if (sharded is not None or args.config == 5) else "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 wave scalars", "data": "synthetic",
-            "config": {"workload": workload, "n_triangles": scene.n_tris, "poses_per_step": POSES_PER_STEP,
-                       "l2": "flushed between timed steps (256 MiB write outside the event pair); mesh+BVH %.0f MB > L2" % (bvh_stats.bvh_bytes / 1e6),
-                       "parallelism": "pose-sharded x%d, BVH replicated" % world,
-                       "bvh_build_ms": bvh_stats.bvh_build_ms, "scene_gen_s": t_scene},
-            "rays_bounces_per_s": world * casts * K / (total_ms_max / 1000.0),
-            "casts_per_step": casts, "image_checksum": img_sum,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": POSES_PER_STEP * 28,
-                    "d2h_bytes_per_step": POSES_PER_STEP * N_CELLS * N_ANGLES},
-            # per launch sequence (one per lane and step): rr_trace_kernel once per pass, rr_scan_kernel between passes, rr_draw_kernel
+            "config": {"workload": wl.describe(scene), "baseline_config": args.config, "n_triangles": scene.n_tris,
+                       "poses_per_step": PPS, "shard": shard,
+                       "l2": "flushed between timed steps (256 MiB write outside the event pair); mesh+BVH %.0f MB > L2" % (st.bvh_bytes / 1e6),
+                       "parallelism": par, "bvh_build_ms": st.bvh_build_ms, "scene_gen_s": t_scene},
+            "rays_bounces_per_s": casts_all * K / (total_ms_max / 1000.0),
+            "casts_per_step": casts_all, "image_checksum": img_sum,
+            "e2e": e2e,
+            # per launch sequence (one per lane and step): rr_prep_kernel, rr_trace_kernel once per pass, rr_scan_kernel between passes, rr_draw_kernel (+ 3 exchange kernels when sharded)
             "gpu_launches": int(launches_timed),
             "wall_s_timed_region": wall,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "rr_trace_kernel", "kernel_ms": trace_ms_sum / max(n_pairs, 1),
-                         "kernel_share_of_step": trace_ms_sum / max(trace_ms_sum + draw_ms_sum, 1e-9),
-                         "algorithmic_bytes_per_launch": trace_bytes,
-                         "formula": "32 B x nodes_visited + 48 B x tris_tested + 4 B x hits per 16-pose step = the %d per-pass launches of rr_trace_kernel (bytes counted by the stats build of the same kernel; kernel_ms = their summed duration incl. the %d rr_scan_kernel launches between them, CUDA events on the launch stream, one lane)" % (N_PASSES, N_PASSES - 1),
-                         "draw_kernel_ms": draw_ms_sum / max(n_pairs, 1), "step_algorithmic_bytes": alg_bytes,
-                         "step_achieved_gbs": alg_bytes / ((total_ms / K) / 1000.0) / 1e9,
-                         "nodes_visited": nodes, "tris_tested": tris},
-            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cpu_cores, "kind": cpu_kind,
+            "roofline": roof,
+            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cpu_cores, "kind": cpu_kind, "kind_detail": CPU_DETAIL[cpu_kind],
                              "sample": ("%d frame(s) of the same workload (pose 0..), OpenMP over azimuths, %.1f s" % (args.cpu_frames, cpu_t))
                              if cpu_fps is not None else "not timed at N > 1 (see the N = 1 line)"},
         }
+        if single_ms is not None:
+            line["single_frame_ms"] = single_ms_max
+        if az_leg is not None:
+            line["azimuth_sharded"] = az_leg
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

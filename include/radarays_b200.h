@@ -260,6 +260,10 @@ int         rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_
  * overlap the other's traversal. 1 = strictly serial launches, which is what rr_kernel_times needs to time a kernel
  * alone. Results do not depend on it. (The reference's counterpart is its OpenMP fan-out, RadarCPU.cpp:155.) */
 int         rr_set_lanes(rr_ctx* ctx, int32_t n_lanes);
+/* on != 0: every following call (host, device-resident, sharded, GenRadarImage) runs the counting instantiation of the
+ * trace kernel, so that rr_get_stats / rr_stats report nodes_visited and tris_tested for exactly the work of that call
+ * (the bench's algorithmic-bytes figure). Slower (single lane, two more counters per ray); results are unchanged. */
+int         rr_set_stats_mode(rr_ctx* ctx, int32_t on);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ SYMBOLS = [
     "rr_set_noise_seed", "rr_simulate", "rr_simulate_motion", "rr_simulate_device", "rr_simulate_stats",
     "rr_debug_trace", "rr_cast_rays", "rr_get_stats", "rr_set_max_waves_per_azimuth", "rr_kernel_times", "rr_set_lanes",
     "rr_get_radar_params", "rr_gen_radar_images", "rr_mesh_load", "rr_mesh_free", "rr_set_mesh_file",
-    "rr_shard_create", "rr_shard_connect", "rr_simulate_sharded", "rr_kernel_launches",
+    "rr_shard_create", "rr_shard_connect", "rr_simulate_sharded", "rr_kernel_launches", "rr_set_stats_mode",
 ]
 
 
@@ -56,6 +56,7 @@ def lib():
     L.rr_set_max_waves_per_azimuth.argtypes = [vp, C.c_uint32]
     L.rr_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i32)]
     L.rr_set_lanes.argtypes = [vp, i32]
+    L.rr_set_stats_mode.argtypes = [vp, i32]
     L.rr_get_radar_params.argtypes = [vp, vp, sz, C.POINTER(sz), C.POINTER(RadarModel)]
     L.rr_gen_radar_images.argtypes = [vp, vp, sz, vp, sz, u64, vp, vp, sz, vp, C.POINTER(Stats)]
     L.rr_shard_create.argtypes = [vp, i32, i32, sz, vp]

@@ -25,7 +25,7 @@ extern "C" cudaError_t rr_launch_peer_exchange(uint32_t* const* peer_flags, int 
 extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStream_t st);
 extern "C" cudaError_t rr_launch_prep(const RRFrameParams* P, cudaStream_t st);
 extern "C" cudaError_t rr_launch_mat_pairs(const float4* materials, int n_mat, int n_tables, RRMatPair* out, cudaStream_t st);
-extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug);
+extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
                                       const float* gs, const float* origins, const float* dirs, size_t n, float tmax,
@@ -41,6 +41,7 @@ struct rr_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = 0;
+    int trace_ctas_per_sm = 0;
     /* scene */
     bool have_mesh = false;
     RRNode* d_nodes = nullptr; float4* d_tris = nullptr;
@@ -79,6 +80,7 @@ struct rr_ctx {
     float4* d_tas = nullptr;
     uint64_t noise_seed = 0;
     uint32_t max_waves_user = 0;
+    int stats_mode = 0;                            /* rr_set_stats_mode: count node visits / triangle tests in every call */
     /* scratch (wavefront lists, rr_internal.h): one set per LANE. A lane is a stream with its own lists; a call's poses
      * are cut into sub-batches that alternate between the lanes, so the tail of one sub-batch's pass (few long rays left)
      * and its draw kernel overlap the other lane's traversal, and device->host copies overlap compute. */
@@ -672,9 +674,8 @@ static int ready(rr_ctx* ctx)
  * items per launch sequence (each lane bounded to ~4 GB of the 180 GB; larger batches run as several sequences). */
 static int ensure_scratch(rr_ctx* ctx, size_t want_items)
 {
-    static int per_sm_cached = 0;                 /* a property of the kernel binary and the device type */
-    if (per_sm_cached < 1) CK(rr_trace_occupancy(&per_sm_cached));
-    const int per_sm = per_sm_cached;
+    if (ctx->trace_ctas_per_sm < 1) CK(rr_trace_occupancy(&ctx->trace_ctas_per_sm));   /* per context = per device */
+    const int per_sm = ctx->trace_ctas_per_sm;
     if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "trace kernel does not fit on an SM");
     const int grid = ctx->num_sms * per_sm;
     const uint32_t S = ctx->model.n_samples, Pn = std::max<uint32_t>(1, ctx->model.n_reflections);
@@ -757,6 +758,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
     /* setter uploads (upload()) are ordered before everything this call launches */
     CK(cudaStreamWaitEvent(st, ctx->upload_ev, 0));
     CK(cudaMemsetAsync(ctx->d_counters, 0, kStatusBytes, st));
+    stats = stats || ctx->stats_mode;
     const int n_total = P.n_poses;
     const int n_lanes = (stats || debug) ? 1 : std::max(1, std::min(ctx->n_lanes, (int)rr_ctx::kLanes));
     const int want_split = std::max(min_split, n_lanes);
@@ -822,7 +824,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
             if (pass + 1 < Pn) { CK(rr_launch_scan(&P, pass + 1, ls)); ctx->launches++; }
         }
         if (timed) CK(cudaEventRecord(te[1], ls));
-        CK(rr_launch_draw(&P, (int)items, (size_t)((P.n_cells + 3) & ~3) * sizeof(float) + (P.n_peers > 0 ? (size_t)P.n_cells : 0), ls, debug));
+        CK(rr_launch_draw(&P, (int)items, ls, debug));
         ctx->launches++;
         if (timed) { CK(cudaEventRecord(te[2], ls)); ctx->tev_count++; }
         if (copy) {
@@ -1069,6 +1071,7 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     if ((rc = ensure_scratch(ctx, ((n_goals + min_split - 1) / min_split) * RR_N_ANGLES))) return rc;
     const size_t img = (size_t)ctx->cfg.n_cells * RR_N_ANGLES;
     CK(regrow(&ctx->d_goal_mat, &ctx->d_goal_mat_cap, mats.size()));
+    CK(regrow(&ctx->d_goal_pairs, &ctx->d_goal_pairs_cap, n_goals * (nm + 1)));
     CK(regrow(&ctx->d_goal_passes, &ctx->d_goal_passes_cap, n_goals));
     if (per_goal_beam) CK(regrow(&ctx->d_goal_beam, &ctx->d_goal_beam_cap, beams.size()));
     CK(regrow(&ctx->d_poses, &ctx->d_poses_cap, n_goals));
@@ -1078,6 +1081,8 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(ctx->d_poses, ctx->h_poses, n_goals * sizeof(rr_pose), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_goal_mat, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(rr_launch_mat_pairs(ctx->d_goal_mat, (int)nm, (int)n_goals, ctx->d_goal_pairs, st));
+    ctx->launches++;
     CK(cudaMemcpyAsync(ctx->d_goal_passes, passes.data(), n_goals * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (per_goal_beam) CK(cudaMemcpyAsync(ctx->d_goal_beam, beams.data(), beams.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     if (real_polar) {
@@ -1093,6 +1098,7 @@ int rr_gen_radar_images(rr_ctx* ctx, const rr_radar_params* goals, size_t n_goal
     P.az_begin = 0; P.az_count = RR_N_ANGLES; P.frame_id0 = frame_id0;
     P.out = ctx->d_out; P.column_major = 0;
     P.materials = ctx->d_goal_mat; P.material_stride = (uint32_t)nm;
+    P.mat_pairs = ctx->d_goal_pairs; P.mat_pair_stride = (uint32_t)(nm + 1);
     if (per_goal_beam) { P.beam_dirs = ctx->d_goal_beam; P.beam_stride = (uint32_t)(3 * S); }
     P.pose_passes = ctx->d_goal_passes;
     RRCopyOut copy;
@@ -1208,6 +1214,13 @@ int rr_set_lanes(rr_ctx* ctx, int32_t n_lanes)
     if (!ctx) return RR_ERR_INVALID_ARGUMENT;
     if (n_lanes < 1 || n_lanes > rr_ctx::kLanes) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_lanes: 1..%d", (int)rr_ctx::kLanes);
     ctx->n_lanes = n_lanes;
+    return RR_OK;
+}
+
+int rr_set_stats_mode(rr_ctx* ctx, int32_t on)
+{
+    if (!ctx) return RR_ERR_INVALID_ARGUMENT;
+    ctx->stats_mode = on ? 1 : 0;
     return RR_OK;
 }
 

@@ -13,6 +13,7 @@
  * rr_detmath.h are shared. Compile with --fmad=false: every fused multiply-add below is explicit.
  */
 #include <algorithm>
+#include <cooperative_groups.h>
 #include "rr_internal.h"
 
 #define RR_FULL 0xffffffffu
@@ -615,153 +616,222 @@ __global__ void __launch_bounds__(RR_SCAN_BLOCK) rr_scan_kernel(const RRFramePar
  * Kernel 3/3: rr_draw_kernel — returns -> range column (RadarCPU.cpp:402-450) -> energy_max, ambient noise,
  * normalise, mono8 (RadarCPU.cpp:453-542). One CTA per (pose, azimuth); the column lives in shared memory.
  *
- * Accumulation is in the reference's order WITHOUT atomics: every bin has exactly one owner thread (its warp by a
- * per-item partition of the column into contiguous 32-bin-granule ranges, its lane by g & 31), so a bin sees its
- * additions in program order = list order and the float column is bit-identical to the sequential reference loop.
- * Returns cluster in range (a wall = a few hundred adjacent bins), so the partition is ADAPTIVE: a shared-memory
- * histogram of splat load per granule is prefix-summed and cut into 8 ranges of equal load. Every warp replays the
- * item's returns pass by pass (the wave lists ARE the signal order); 32 waves are tested at once (ballot) and only
- * the returns overlapping the warp's range are applied.
+ * The reference adds every return's window of W weighted bins in list order, so a bin's float value depends on the ORDER
+ * of the additions that reach it (and on nothing else: bins are independent). The kernel keeps that order per bin without
+ * atomics and without replaying the list:
+ *   1. count   — every return adds 1 to each 32-bin granule its window overlaps (integer shared-memory atomics, any order);
+ *   2. scan    — granule counts -> offsets of per-granule entry lists;
+ *   3. fill    — the returns are appended to the lists of their granules IN LIST ORDER: each warp owns a contiguous
+ *                quarter of the list (its own cursors, offset by the counts of the quarters before it) and appends 32
+ *                returns per step, granule by granule (warp min-reduction picks the next granule, a ballot gives every
+ *                lane its rank), so list order = order inside every granule list;
+ *   4. add     — a warp takes a granule (dynamic queue), lane <-> bin, the bin's value sits in a REGISTER while the lane
+ *                walks the granule's list front to back: one broadcast shared-memory load per entry, the dependent
+ *                add chain of the reference and nothing else. A window only engages the lanes of the granules it
+ *                overlaps; no return is ever looked at by a warp that has no bin in its window.
+ * Lists longer than the entry buffer (many passes / wide kernels) are processed in chunks of the return list; the column
+ * stays in shared memory between chunks.
+ * Epilogue per cell, then the mono8 column goes out as
+ *   RR_OUT_CLUSTER  8 CTAs = 8 adjacent azimuths form a thread-block cluster: each CTA reads the 8 byte columns through
+ *                   distributed shared memory for its eighth of the cells and stores 8-byte row segments of the
+ *                   row-major image (the reference's cv::Mat, Radar.cpp:34) instead of single bytes at stride 400;
+ *   RR_OUT_BYTES    the same image with byte stores (shards whose column range is not a multiple of 8, odd scroll);
+ *   RR_OUT_COLUMNS  column-major shard / NVLink peer stores (16-byte vectors).
  * ---------------------------------------------------------------------------------------------- */
-template <bool DEBUG, bool PEERS>
+#ifndef RR_DRAW_ENTRIES
+#define RR_DRAW_ENTRIES 2048          /* (start, strength) entries of a chunk: 16 KB */
+#endif
+#define RR_DRAW_CLUSTER 8
+enum { RR_OUT_CLUSTER = 0, RR_OUT_BYTES = 1, RR_OUT_COLUMNS = 2 };
+
+template <bool DEBUG, int OUT>
 __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P)
 {
-    extern __shared__ __align__(16) float s_col[];       /* n_cells floats: this azimuth's range column (+ its mono8 bytes when sharded) */
-    uint8_t* s_bytes = PEERS ? reinterpret_cast<uint8_t*>(s_col + ((P.n_cells + 3) & ~3)) : nullptr;
+    extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ double s_weights[RR_MAX_DENOISE];         /* float weights widened once (the splat multiplies in double) */
     __shared__ unsigned char s_perm[256];
     __shared__ double2 s_grad[256];
     __shared__ float s_red[RR_WARPS];
-    __shared__ uint32_t s_load[RR_MAX_GRANULES];
-    __shared__ int s_bound[RR_WARPS + 1];
-    __shared__ uint32_t s_begin[RR_MAX_PASSES], s_end[RR_MAX_PASSES];
+    __shared__ uint32_t s_begin[RR_MAX_PASSES], s_voff[RR_MAX_PASSES + 1];
+    __shared__ uint32_t s_total, s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t item = blockIdx.x;
     const int pose_i = (int)(item / (uint32_t)P.az_count);
     const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
-    const int C = P.n_cells;
+    const int C = P.n_cells, C4 = (C + 3) & ~3;
     const int n_passes = P.n_passes;
+    const int n_gran = (C + 31) >> 5, G1 = n_gran + 1;           /* <= 313 granules for n_cells <= 10000 */
+    float* s_col = reinterpret_cast<float*>(s_raw);                                    /* [C4] this azimuth's range column   */
+    uint2* s_ent = reinterpret_cast<uint2*>(s_raw + (size_t)C4 * 4);                   /* [RR_DRAW_ENTRIES] (start, strength) */
+    uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_ent);                              /* [C4] mono8 column, after the lists  */
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_raw + (size_t)C4 * 4 + (size_t)RR_DRAW_ENTRIES * 8);   /* [RR_WARPS + 1][G1] */
+    uint32_t* s_off = s_cnt + RR_WARPS * G1;                                           /* [G1] list offsets                   */
+
     for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? (double)P.denoise_weights[i] : 0.0;
     for (int i = tid; i < 256; i += RR_BLOCK) { s_perm[i] = c_perlin_perm[i]; s_grad[i] = rr_pgrad_coef(c_perlin_perm[i]); }
-    const int n_gran = (C + 31) >> 5;                              /* <= 313 for n_cells <= 10000 */
-    for (int i = tid; i < C; i += RR_BLOCK) s_col[i] = 0.0f;
-    for (int i = tid; i < RR_MAX_GRANULES; i += RR_BLOCK) s_load[i] = 0u;
-    if (tid < n_passes) {                                          /* this item's run of every pass list */
+    for (int i = tid; i < C4; i += RR_BLOCK) s_col[i] = 0.0f;
+    if (tid == 0) {                                                /* this item's run of every pass list, concatenated */
         const uint32_t S = (uint32_t)P.n_samples;
-        uint32_t b, e, lim;
-        if (tid == 0) { b = item * S; e = b + S; lim = (uint32_t)P.n_items * S; }
-        else {
-            const uint32_t* is = P.item_start + (size_t)tid * P.item_stride;
-            b = is[item]; e = is[item + 1]; lim = min(P.pass_total[tid], P.wave_cap);
+        uint32_t run = 0;
+        for (int p = 0; p < n_passes; p++) {
+            uint32_t b, e, lim;
+            if (p == 0) { b = item * S; e = b + S; lim = (uint32_t)P.n_items * S; }
+            else {
+                const uint32_t* is = P.item_start + (size_t)p * P.item_stride;
+                b = is[item]; e = is[item + 1]; lim = min(P.pass_total[p], P.wave_cap);
+            }
+            b = min(b, lim); e = max(b, min(e, lim));
+            s_begin[p] = b; s_voff[p] = run; run += e - b;
         }
-        s_begin[tid] = min(b, lim); s_end[tid] = min(e, lim);
+        s_voff[n_passes] = run;
     }
     __syncthreads();
+    const uint32_t n_slots = s_voff[n_passes];
 
     const int W = P.denoise_on ? P.denoise_width : 1;
     const int mode = P.denoise_on ? P.denoise_mode : 0;
     const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
+    const int max_gr = (W + 30) / 32 + 1;                          /* granules one window can overlap */
+    const uint32_t ch_safe = max(16u, ((uint32_t)RR_DRAW_ENTRIES / (2u * (uint32_t)max_gr)) & ~15u);
 
-    /* ---- 1. splat load per 32-bin granule (any order: integer atomics) */
-    for (int pass = 0; pass < n_passes; pass++) {
-        const int2* pc = P.sig_cell + (size_t)pass * P.wave_cap;
-        for (uint32_t k = s_begin[pass] + tid; k < s_end[pass]; k += RR_BLOCK) {
-            const int2 cc = pc[k];
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int cell = q ? cc.y : cc.x;
-                if (!(cell < C) || !(cell > -RR_MAX_DENOISE - 1)) continue;
-                const int st = cell - mode;
-                const int g_lo = max(st, lo_bin) >> 5, g_hi = (min(st + W, C) - 1) >> 5;
-                for (int g = g_lo; g <= g_hi; g++) atomicAdd(&s_load[g], 1u);
-            }
+    /* virtual slot v of the concatenated list -> (pass, position in the pass list) */
+    auto locate = [&](uint32_t v, int& p, uint32_t& k) {
+        p = 0;
+        while (p + 1 < n_passes && v >= s_voff[p + 1]) p++;
+        k = s_begin[p] + (v - s_voff[p]);
+    };
+    /* window of a return: bins [max(st, lo_bin), min(st + W, C)), st = cell - mode; cell < C (:414); very negative cells
+     * (no return, time = -inf/NaN) can not reach a bin */
+    auto window = [&](int cell, int& g_lo, int& g_hi) -> bool {
+        if (!(cell < C) || !(cell > -RR_MAX_DENOISE - 1)) return false;
+        const int st = cell - mode;
+        const int lo = max(st, lo_bin), hi = min(st + W, C);
+        if (lo >= hi) return false;
+        g_lo = lo >> 5; g_hi = (hi - 1) >> 5;
+        return true;
+    };
+
+    float m = 0.0f;                                                /* running max_val (:428-431), per lane */
+    uint32_t c0 = 0, ch = n_slots;                                 /* first attempt: the whole list as one chunk */
+    while (c0 < n_slots) {
+        const uint32_t c1 = min(n_slots, c0 + ch);
+        const uint32_t n_ret = 2u * (c1 - c0);                     /* two return slots per wave */
+        const uint32_t nb = (n_ret + 31u) >> 5;                    /* steps of 32 returns */
+        const uint32_t bpw = (nb + RR_WARPS - 1) / RR_WARPS;       /* steps per warp (contiguous quarters) */
+        for (int i = tid; i < (RR_WARPS + 1) * G1; i += RR_BLOCK) s_cnt[i] = 0u;
+        if (tid == 0) s_next = 0u;
+        __syncthreads();
+        /* ---- 1. count */
+        for (uint32_t e = tid; e < n_ret; e += RR_BLOCK) {
+            int p; uint32_t k;
+            locate(c0 + (e >> 1), p, k);
+            const int cell = __ldg(reinterpret_cast<const int*>(P.sig_cell + (size_t)p * P.wave_cap) + 2 * (size_t)k + (e & 1u));
+            int g_lo, g_hi;
+            if (!window(cell, g_lo, g_hi)) continue;
+            uint32_t* cw = s_cnt + ((e >> 5) / bpw) * G1;
+            for (int g = g_lo; g <= g_hi; g++) atomicAdd(&cw[g], 1u);
         }
-    }
-    __syncthreads();
-    /* ---- 2. cut the granules into RR_WARPS contiguous ranges of (nearly) equal load */
-    if (wid == 0) {
-        uint32_t run = 0;                                             /* inclusive prefix over granules, 32 at a time */
-        uint32_t total = 0;
-        for (int base = 0; base < n_gran; base += 32) total += __reduce_add_sync(RR_FULL, (base + lane < n_gran) ? s_load[base + lane] : 0u);
-        if (lane <= RR_WARPS) s_bound[lane] = (lane == RR_WARPS) ? n_gran : 0;
-        __syncwarp();
-        for (int base = 0; base < n_gran; base += 32) {
-            const uint32_t v = (base + lane < n_gran) ? s_load[base + lane] : 0u;
-            uint32_t incl = v;
+        __syncthreads();
+        /* ---- 2. scan: list offsets per granule; every warp's cursor starts behind the earlier quarters' entries */
+        if (wid == 0) {
+            uint32_t run = 0;
+            for (int base = 0; base < n_gran; base += 32) {
+                const int g = base + lane;
+                uint32_t c[RR_WARPS], tot = 0;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const uint32_t nb = __shfl_up_sync(RR_FULL, incl, off); if (lane >= off) incl += nb; }
-            const uint32_t before = run + incl - v, after = run + incl;
-            /* granule (base+lane) opens range w when the load before it is <= w*total/8 < load after it */
-            if (base + lane < n_gran && v > 0) {
-                for (int w = 1; w < RR_WARPS; w++) {
-                    const uint32_t cut = (uint32_t)(((unsigned long long)total * (unsigned)w) / RR_WARPS);
-                    if (before <= cut && cut < after) s_bound[w] = base + lane + ((cut - before) * 2 >= v ? 1 : 0);
+                for (int w = 0; w < RR_WARPS; w++) { c[w] = (g < n_gran) ? s_cnt[w * G1 + g] : 0u; tot += c[w]; }
+                uint32_t incl = tot;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const uint32_t nb2 = __shfl_up_sync(RR_FULL, incl, off); if (lane >= off) incl += nb2; }
+                uint32_t o = run + incl - tot;
+                if (g < n_gran) {
+                    s_off[g] = o;
+#pragma unroll
+                    for (int w = 0; w < RR_WARPS; w++) { s_cnt[w * G1 + g] = o; o += c[w]; }
+                }
+                run += __shfl_sync(RR_FULL, incl, 31);
+            }
+            if (lane == 0) { s_off[n_gran] = run; s_total = run; }
+        }
+        __syncthreads();
+        if (s_total > (uint32_t)RR_DRAW_ENTRIES) {                 /* whole list too long for the buffer: chunks (uniform branch) */
+            __syncthreads();                                       /* everybody has read s_total */
+            ch = ch_safe;                                          /* <= RR_DRAW_ENTRIES entries by construction */
+            continue;
+        }
+        /* ---- 3. fill, in list order */
+        {
+            uint32_t* cur = s_cnt + wid * G1;
+            const uint32_t b_end = min(nb, (uint32_t)(wid + 1) * bpw);
+            for (uint32_t b = (uint32_t)wid * bpw; b < b_end; b++) {
+                const uint32_t e = (b << 5) + (uint32_t)lane;
+                int next = INT32_MAX, g_hi = -1, st = 0;
+                uint32_t sv = 0u;
+                if (e < n_ret) {
+                    int p; uint32_t k;
+                    locate(c0 + (e >> 1), p, k);
+                    const size_t idx = 2 * (size_t)k + (e & 1u);
+                    const int cell = __ldg(reinterpret_cast<const int*>(P.sig_cell + (size_t)p * P.wave_cap) + idx);
+                    int g_lo;
+                    if (window(cell, g_lo, g_hi)) {
+                        next = g_lo; st = cell - mode;
+                        sv = __ldg(reinterpret_cast<const uint32_t*>(P.sig_strength + (size_t)p * P.wave_cap) + idx);
+                    }
+                }
+                for (;;) {
+                    const int g = __reduce_min_sync(RR_FULL, next);
+                    if (g == INT32_MAX) break;
+                    const bool mine = (next == g);
+                    const uint32_t mm = __ballot_sync(RR_FULL, mine);
+                    const uint32_t base = cur[g];
+                    if (mine) {
+                        s_ent[base + __popc(mm & lt_mask)] = make_uint2((uint32_t)st, sv);
+                        next = (g < g_hi) ? g + 1 : INT32_MAX;
+                    }
+                    __syncwarp();
+                    if (lane == 0) cur[g] = base + __popc(mm);
+                    __syncwarp();
                 }
             }
-            run += __shfl_sync(RR_FULL, incl, 31);
         }
-        __syncwarp();
-        if (lane == 0) {                                              /* monotone, inside [0, n_gran] */
-            int prev = 0;
-            for (int w = 1; w < RR_WARPS; w++) { int bnd = (total == 0) ? (w * n_gran) / RR_WARPS : s_bound[w]; bnd = max(prev, min(bnd, n_gran)); s_bound[w] = bnd; prev = bnd; }
-        }
-    }
-    __syncthreads();
-    const int my_lo = s_bound[wid] << 5, my_hi = min(C, s_bound[wid + 1] << 5);   /* this warp's bins [my_lo, my_hi) */
-
-    /* ---- 3. ordered accumulation */
-    float m = 0.0f;
-    auto bin_update = [&](const int g, const int st, const float sv, const double svd) {
-        float v;
-        if (P.denoise_on) {
-            v = (float)((double)s_col[g] + svd * s_weights[g - st]);
-        } else {
-            const float old = s_col[g];
-            v = (old < sv) ? sv : old;                                 /* std::max(old, strength), :439 */
-        }
-        s_col[g] = v;
-        if (v > m) m = v;                                              /* running max_val, :428-431 */
-    };
-    auto splat = [&](const int st, const float sv) {
-        const double svd = (double)sv;
-        const int lo = max(max(st, lo_bin), my_lo), hi = min(min(st + W, C), my_hi);
-        int g = lo + ((lane - lo) & 31);                               /* bin g <-> lane g & 31, always */
-        /* a window of W bins gives a lane 0, 1 or (W > 32) 2.. bins: spelled out so that the common cases cost no loop */
-        if (g < hi) {
-            bin_update(g, st, sv, svd);
-            g += 32;
-            if (g < hi) {
-                bin_update(g, st, sv, svd);
-#pragma unroll 1
-                for (g += 32; g < hi; g += 32) bin_update(g, st, sv, svd);
-            }
-        }
-    };
-    if (my_lo < my_hi) {
-        for (int pass = 0; pass < n_passes; pass++) {
-            const int2* pc = P.sig_cell + (size_t)pass * P.wave_cap;
-            const float2* pst = P.sig_strength + (size_t)pass * P.wave_cap;
-            const uint32_t e = s_end[pass];
-            for (uint32_t base = s_begin[pass]; base < e; base += 32) {
-                const bool valid = base + lane < e;
-                const int2 cc = valid ? pc[base + lane] : make_int2(INT32_MIN, INT32_MIN);
-                /* cell < C (:414); very negative cells (no return, time = -inf/NaN) can not reach a bin */
-                const int start0 = cc.x - mode, start1 = cc.y - mode;
-                const bool rel0 = (cc.x < C) && (cc.x > -RR_MAX_DENOISE - 1) && (max(start0, lo_bin) < my_hi) && (min(start0 + W, C) > my_lo);
-                const bool rel1 = (cc.y < C) && (cc.y > -RR_MAX_DENOISE - 1) && (max(start1, lo_bin) < my_hi) && (min(start1 + W, C) > my_lo);
-                float2 str = make_float2(0.f, 0.f);
-                if (rel0 || rel1) str = pst[base + lane];
-                uint32_t mask0 = __ballot_sync(RR_FULL, rel0), mask1 = __ballot_sync(RR_FULL, rel1);
-                while (mask0 | mask1) {
-                    const int j = __ffs(mask0 | mask1) - 1;
-                    const uint32_t bit = 1u << j;
-                    if (mask0 & bit) splat(__shfl_sync(RR_FULL, start0, j), __shfl_sync(RR_FULL, str.x, j));
-                    if (mask1 & bit) splat(__shfl_sync(RR_FULL, start1, j), __shfl_sync(RR_FULL, str.y, j));
-                    mask0 &= ~bit; mask1 &= ~bit;
+        __syncthreads();
+        /* ---- 4. add: lane <-> bin, value in a register, list front to back */
+        for (;;) {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(&s_next, 1u);
+            g = __shfl_sync(RR_FULL, g, 0);
+            if (g >= (uint32_t)n_gran) break;
+            const uint32_t eb = s_off[g], ee = s_off[g + 1];
+            if (eb == ee) continue;
+            const int bin = (int)(g << 5) + lane;
+            const bool live = (bin >= lo_bin) && (bin < C);
+            float acc = live ? s_col[bin] : 0.0f;
+            if (P.denoise_on) {
+#pragma unroll 4
+                for (uint32_t e = eb; e < ee; e++) {
+                    const uint2 en = s_ent[e];
+                    const uint32_t k = (uint32_t)(bin - (int)en.x);
+                    if (live && k < (uint32_t)W) {
+                        acc = (float)((double)acc + (double)__uint_as_float(en.y) * s_weights[k]);
+                        if (acc > m) m = acc;
+                    }
+                }
+            } else {
+                for (uint32_t e = eb; e < ee; e++) {
+                    const uint2 en = s_ent[e];
+                    if (live && bin == (int)en.x) {
+                        const float sv = __uint_as_float(en.y);
+                        acc = (acc < sv) ? sv : acc;               /* std::max(old, strength), :439 */
+                        if (acc > m) m = acc;
+                    }
                 }
             }
+            if (live) s_col[bin] = acc;
         }
+        __syncthreads();
+        c0 = c1;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) { const float o2 = __shfl_xor_sync(RR_FULL, m, off); if (o2 > m) m = o2; }
@@ -783,9 +853,7 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
         ? (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 0u) * 1000.0 : 0.0;
     const float out_scale = (float)(P.signal_max / (double)max_val);
     const double ycoord1 = (double)col * 0.05, ycoord2 = (double)col * 0.2;
-    uint8_t* out = P.column_major
-        ? P.out + ((size_t)pose_i * P.az_count + (size_t)(az - P.az_begin)) * (size_t)C
-        : P.out + (size_t)pose_i * (size_t)C * RR_N_ANGLES + col;
+    uint8_t* out_rows = P.out + (size_t)pose_i * (size_t)C * RR_N_ANGLES + col;
     for (int i = tid; i < C; i += RR_BLOCK) {
         float v = s_col[i] * P.energy_max_f;
         if (P.ambient_noise) {
@@ -808,16 +876,43 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
         v = v * out_scale;
         if (DEBUG && P.dbg_columns) P.dbg_columns[(size_t)az * C + i] = v;
         const uint8_t px = rr_to_u8(v);
-        if (PEERS) s_bytes[i] = px;
-        else if (P.column_major) out[i] = px;
-        else out[(size_t)i * RR_N_ANGLES] = px;
+        if (OUT == RR_OUT_BYTES) out_rows[(size_t)i * RR_N_ANGLES] = px;
+        else s_bytes[i] = px;
     }
-    if (PEERS) {
-        /* the finished mono8 column goes to every rank's gather buffer with 16-byte peer stores (NVLink) */
+    if (OUT == RR_OUT_CLUSTER) {
+        /* 8 adjacent azimuths -> 8-byte row segments. The launcher guarantees: az_count % 8 == 0 (a cluster never
+         * straddles two poses), (scroll_image + az_begin) % 8 == 0 (segments are aligned and never wrap at column 400)
+         * and an 8-byte aligned image. */
+        namespace cg = cooperative_groups;
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();
+        const unsigned r = cl.block_rank();
+        const uint32_t* rem[RR_DRAW_CLUSTER];
+#pragma unroll
+        for (int j = 0; j < RR_DRAW_CLUSTER; j++) rem[j] = reinterpret_cast<const uint32_t*>(cl.map_shared_rank(s_bytes, j));
+        const int n_words = C4 >> 2, wpr = (n_words + RR_DRAW_CLUSTER - 1) / RR_DRAW_CLUSTER;
+        const int w_end = min(n_words, (int)(r + 1) * wpr);
+        uint8_t* seg = out_rows - r;                                /* column of the cluster's first azimuth */
+        for (int w = (int)r * wpr + tid; w < w_end; w += RR_BLOCK) {
+            uint32_t x[RR_DRAW_CLUSTER];
+#pragma unroll
+            for (int j = 0; j < RR_DRAW_CLUSTER; j++) x[j] = rem[j][w];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int cell = 4 * w + i;
+                if (cell < C) {
+                    const uint32_t sel = (uint32_t)i | ((uint32_t)(4 + i) << 4);
+                    const uint32_t lo = __byte_perm(__byte_perm(x[0], x[1], sel), __byte_perm(x[2], x[3], sel), 0x5410);
+                    const uint32_t hi = __byte_perm(__byte_perm(x[4], x[5], sel), __byte_perm(x[6], x[7], sel), 0x5410);
+                    *reinterpret_cast<uint2*>(seg + (size_t)cell * RR_N_ANGLES) = make_uint2(lo, hi);
+                }
+            }
+        }
+        cl.sync();                                                  /* nobody leaves while its column is still being read */
+    }
+    if (OUT == RR_OUT_COLUMNS) {
         __syncthreads();
-        const size_t col_off = ((size_t)(P.peer_pose0 + (uint32_t)pose_i) * RR_N_ANGLES + (size_t)az) * (size_t)C;
-        for (int p = 0; p < P.n_peers; p++) {
-            uint8_t* dst = P.peer_out[p] + col_off;
+        auto copy_column = [&](uint8_t* dst) {
             if (((C & 15) == 0) && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
                 const uint4* src4 = reinterpret_cast<const uint4*>(s_bytes);
                 uint4* dst4 = reinterpret_cast<uint4*>(dst);
@@ -825,9 +920,15 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
             } else {
                 for (int k = tid; k < C; k += RR_BLOCK) dst[k] = s_bytes[k];
             }
+        };
+        if (P.n_peers > 0) {
+            /* the finished mono8 column goes to every rank's gather buffer with 16-byte peer stores (NVLink) */
+            const size_t col_off = ((size_t)(P.peer_pose0 + (uint32_t)pose_i) * RR_N_ANGLES + (size_t)az) * (size_t)C;
+            for (int p = 0; p < P.n_peers; p++) copy_column(P.peer_out[p] + col_off);
+        } else {
+            copy_column(P.out + ((size_t)pose_i * P.az_count + (size_t)(az - P.az_begin)) * (size_t)C);
         }
     }
-
 }
 
 /* Sum of squared pixel differences of every rendered goal image against a recorded ("real") polar image: the data
@@ -985,17 +1086,38 @@ extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStre
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, size_t smem, cudaStream_t st, int debug)
+extern "C" size_t rr_draw_smem_bytes(int n_cells)
 {
-    static bool attr_done = false;                     /* 10000 cells + their mono8 bytes (sharded mode) exceed 48 KB with the static tables */
-    if (!attr_done) {
-        cudaFuncSetAttribute(rr_draw_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
+    const size_t c4 = (size_t)((n_cells + 3) & ~3), g1 = (size_t)((n_cells + 31) >> 5) + 1;
+    return c4 * 4 + (size_t)RR_DRAW_ENTRIES * 8 + (size_t)(RR_WARPS + 1) * g1 * 4;
+}
+
+template <bool DEBUG, int OUT>
+static cudaError_t rr_draw_launch_one(const RRFrameParams& P, int n_items, size_t smem, cudaStream_t st)
+{
+    /* more than 48 KB of dynamic shared memory is an opt-in per function AND per device: cheap enough to repeat per launch */
+    cudaError_t e = cudaFuncSetAttribute(rr_draw_kernel<DEBUG, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_items); cfg.blockDim = dim3(RR_BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (OUT == RR_OUT_CLUSTER) {
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = RR_DRAW_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
     }
-    if (P->n_peers > 0) rr_draw_kernel<false, true><<<n_items, RR_BLOCK, smem, st>>>(*P);
-    else if (debug) rr_draw_kernel<true, false><<<n_items, RR_BLOCK, smem, st>>>(*P);
-    else rr_draw_kernel<false, false><<<n_items, RR_BLOCK, smem, st>>>(*P);
-    return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, rr_draw_kernel<DEBUG, OUT>, P);
+}
+
+extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, cudaStream_t st, int debug)
+{
+    const size_t smem = rr_draw_smem_bytes(P->n_cells);
+    if (P->n_peers > 0 || P->column_major) return rr_draw_launch_one<false, RR_OUT_COLUMNS>(*P, n_items, smem, st);
+    /* row-major image: 8-byte row segments through a cluster of 8 azimuths when the columns of a cluster are aligned */
+    const bool aligned = (P->az_count % RR_DRAW_CLUSTER == 0) && ((P->scroll_image + P->az_begin) % RR_DRAW_CLUSTER == 0)
+                         && ((reinterpret_cast<size_t>(P->out) & 7) == 0) && !getenv("RR_DRAW_NO_CLUSTER");
+    if (debug) return aligned ? rr_draw_launch_one<true, RR_OUT_CLUSTER>(*P, n_items, smem, st) : rr_draw_launch_one<true, RR_OUT_BYTES>(*P, n_items, smem, st);
+    return aligned ? rr_draw_launch_one<false, RR_OUT_CLUSTER>(*P, n_items, smem, st) : rr_draw_launch_one<false, RR_OUT_BYTES>(*P, n_items, smem, st);
 }
 
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm)

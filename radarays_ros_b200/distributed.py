@@ -85,6 +85,38 @@ class ShardedRadar:
         self.radar.simulate_sharded(d_pose.data_ptr(), 1, d_img.data_ptr(), frame_id=frame_id, stream=stream.cuda_stream)
         return d_img
 
+    def simulate_batch_nccl(self, d_poses, d_out, frame_id=0, stream=None):
+        """Batch of frames, device to device, exchange = ONE NCCL all_gather of the column-major shards:
+        d_poses: torch float32 [n, 7] on the device, d_out: torch uint8 [n, n_cells, 400] (the full images, every rank).
+        The assembly (concatenate shards along the azimuth axis, transpose to the reference's row-major layout, apply
+        scroll_image) runs on the device. This is the library-collective variant the fused peer-store path is measured
+        against (bench.py --exchange nccl)."""
+        import torch
+        import torch.distributed as dist
+        cfg = self.radar.m_cfg
+        n, C = d_poses.shape[0], cfg.n_cells
+        stream = stream or torch.cuda.current_stream(d_poses.device)
+        counts = [azimuth_shard(r, self.world)[1] for r in range(self.world)]
+        cmax = max(counts)
+        with torch.cuda.stream(stream):
+            # shard buffer padded to the largest shard: [n][cmax][C]; the kernel writes [n][count][C] contiguously
+            mine = torch.empty((n, self.count, C), dtype=torch.uint8, device=d_poses.device)
+            self.radar.simulate_device(d_poses.data_ptr(), n, mine.data_ptr(), frame_id=frame_id, azimuth_begin=self.begin,
+                                       azimuth_count=self.count, column_major=True, stream=stream.cuda_stream)
+            if self.count < cmax:
+                mine = torch.cat([mine, torch.zeros((n, cmax - self.count, C), dtype=torch.uint8, device=mine.device)], dim=1)
+            gathered = torch.empty((self.world, n, cmax, C), dtype=torch.uint8, device=mine.device)
+            if self.world > 1:
+                dist.all_gather_into_tensor(gathered, mine.contiguous(), group=self.group)
+            else:
+                gathered[0] = mine
+            cols = torch.cat([gathered[r, :, :counts[r], :] for r in range(self.world)], dim=1)     # [n][400][C]
+            img = cols.permute(0, 2, 1)                                                              # [n][C][400]
+            if cfg.scroll_image % N_ANGLES:
+                img = torch.roll(img, shifts=cfg.scroll_image % N_ANGLES, dims=2)
+            d_out.copy_(img)
+        return d_out
+
     def simulate(self, pose, frame_id=0):
         import torch
         dev = torch.device("cuda", self.radar.device)

@@ -132,6 +132,10 @@ class RadarB200:
         """1 = strictly serial kernel launches (per-kernel timing); default 2 overlaps sub-batches of a call."""
         capi.check(self._ctx, self._lib.rr_set_lanes(self._ctx, n))
 
+    def setStatsMode(self, on):
+        """Count node visits / triangle tests in every following call (get_stats); see rr_set_stats_mode."""
+        capi.check(self._ctx, self._lib.rr_set_stats_mode(self._ctx, 1 if on else 0))
+
     # ---- the hot path --------------------------------------------------------------------------------------------
     @staticmethod
     def _poses(poses):

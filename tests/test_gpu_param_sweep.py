@@ -36,7 +36,7 @@ def _cases(n=18, seed=20240310):
             ambient_noise_energy_min=float(rng.uniform(0.0, 0.05)), ambient_noise_energy_loss=float(rng.uniform(0.0, 0.2)),
             energy_max=float(rng.uniform(0.2, 1.0)), signal_max=float(rng.uniform(50.0, 255.0)),
             scroll_image=int(rng.integers(0, 400)), record_multi_reflection=int(rng.integers(0, 2)),
-            record_multi_path=int(rng.integers(0, 2)), multipath_threshold=float(rng.uniform(-0.5, 0.9)), include_motion=0)
+            record_multi_path=int(rng.integers(0, 2)), multipath_threshold=float(rng.uniform(0.0, 0.9)), include_motion=0)
         out.append((scene, cfg, int(rng.integers(0, 1000)), int(rng.integers(0, 1000)), int(rng.integers(0, 4))))
     return out
 
