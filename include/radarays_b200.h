@@ -34,6 +34,7 @@ typedef enum {
     RR_ERR_OUT_OF_RANGE = -4,      /* material or object id out of bounds (quirk 17 of SURVEY.md) */
     RR_ERR_WAVE_OVERFLOW = -5,     /* per-azimuth wave list exceeded max_waves_per_azimuth */
     RR_ERR_NO_DEVICE = -6,
+    RR_ERR_PEER_TIMEOUT = -8,      /* rr_simulate_sharded: a rank's columns did not arrive (RR_PEER_TIMEOUT_MS, default 5000); sticky until reported */
     RR_ERR_OUT_OF_MEMORY = -7      /* host allocation failed / a size in the input is absurd; no C++ exception ever crosses this ABI */
 } rr_status;
 
@@ -221,7 +222,10 @@ int         rr_cast_rays(rr_ctx* ctx, const float* origins_xyz, const float* dir
  *   rr_shard_create   allocates this rank's gather buffer (max_poses frames) and returns its IPC handle
  *   rr_shard_connect  takes the handles of all ranks (rank order, e.g. from an all_gather of the 64-byte handles)
  *   rr_simulate_sharded  device-resident poses in, the FULL image(s) out on every rank; enqueued on `cuda_stream`,
- *                     not synchronised. All ranks must call it with the same poses, frame ids and parameters. */
+ *                     not synchronised. All ranks must call it with the same poses, frame ids and parameters.
+ *                     A rank whose columns do not arrive within RR_PEER_TIMEOUT_MS (environment, default 5000) leaves the
+ *                     frame incomplete: the NEXT rr_simulate_sharded / rr_get_stats call on the waiting rank returns
+ *                     RR_ERR_PEER_TIMEOUT (the flag is sticky until it has been reported once). */
 #define RR_MAX_PEERS 8
 typedef struct { unsigned char opaque[64]; } rr_ipc_handle;
 int         rr_shard_create(rr_ctx* ctx, int32_t rank, int32_t world, size_t max_poses, rr_ipc_handle* handle_out);

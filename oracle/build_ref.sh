@@ -8,7 +8,7 @@ REF="${RADARAYS_REFERENCE:-/root/reference}"
 [ -d "$REF/src/radarays_ros" ] || { echo "build_ref.sh: $REF not present, skipping"; exit 0; }
 mkdir -p "$HERE/_ref"
 CXX="${HOSTCXX:-/usr/bin/g++}"
-FLAGS="-O2 -std=c++17 -fPIC -fopenmp -ffp-contract=off -mfma -w -include $HERE/ref_shim/pre.h -I$HERE/ref_shim -I$REF/include"
+FLAGS="-O3 -march=x86-64-v3 -std=c++17 -fPIC -fopenmp -ffp-contract=off -mfma -w -include $HERE/ref_shim/pre.h -I$HERE/ref_shim -I$REF/include"
 for f in RadarCPU Radar radar_algorithms; do
   $CXX $FLAGS -c "$REF/src/radarays_ros/$f.cpp" -o "$HERE/_ref/$f.o"
 done

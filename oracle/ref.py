@@ -27,8 +27,19 @@ def lib():
         L.ref_simulate.argtypes = [C.c_void_p, C.POINTER(RadarModelConfig), C.POINTER(RadarModel), C.c_void_p, C.c_size_t,
                                    C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                    C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_sample_cone_local.restype = C.c_int
+        L.ref_sample_cone_local.argtypes = [C.c_float, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+def sample_cone_local(width_rad, n_samples, sample_dist, p_in_cone, seed):
+    """The reference's own sample_cone_local (radar_algorithms.cpp:248-294) fed from the Philox stream the oracle and the
+    library draw from: (n_samples, 3) float32 directions in DRAW order."""
+    out = np.zeros((n_samples, 3), np.float32)
+    n = lib().ref_sample_cone_local(width_rad, n_samples, sample_dist, p_in_cone, seed, _ptr(out))
+    assert n == n_samples
+    return out
 
 
 def _ptr(a):

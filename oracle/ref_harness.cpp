@@ -4,6 +4,8 @@
  * (src/radar_simulator.cpp:83-96,145-158): construct the backend, deliver parameters, call simulate(). */
 #include <radarays_ros/RadarCPU.hpp>
 #include <radarays_ros/ros_helper.h>
+#include <radarays_ros/radar_algorithms.h>
+#include <radarays_ros/radar_math.h>
 #include <omp.h>
 #include <sstream>
 #include "../include/radarays_b200.h"     /* POD layouts of the C interface only */
@@ -12,6 +14,9 @@ namespace rr_ref_shim {
 static NoiseState g_noise;
 NoiseState& noise_state() { return g_noise; }
 thread_local uint32_t tls_azimuth = 0;
+thread_local BeamState tls_beam;
+/* standard normal draw = the reference's own quantile() (radar_math.h:47-50) of an open-interval uniform */
+float std_normal_from_bits(uint32_t bits) { return radarays_ros::quantile(((float)(bits >> 9) + 0.5f) * 0x1p-23f); }
 }
 
 /* ros_helper.cpp (XmlRpc parsing) is not compiled; this is the one function of it Radar::loadParams calls */
@@ -153,6 +158,24 @@ int ref_simulate(void* h, const rr_config* cfg, const rr_model* model,
     if (!msg) return 1;
     if (out_polar) std::memcpy(out_polar, msg->data.data(), msg->data.size());
     return 0;
+}
+
+/* The reference's OWN sample_cone_local (radar_algorithms.cpp:248-294), its std::mt19937 / distributions replaced by the
+ * Philox-fed shims of pre.h: pins oracle::sample_cone_local and the library's draw_beam_samples (as SETS of directions:
+ * both store the i.i.d. draws along a Morton curve, the reference in draw order). */
+int ref_sample_cone_local(float width, int n_samples, int sample_dist, float p_in_cone, uint64_t seed, float* dirs_out)
+{
+    radarays_ros::DirectedWave wave;
+    wave.energy = 1.0; wave.polarization = 0.5; wave.frequency = 76.5; wave.velocity = 0.3;
+    wave.material_id = 0; wave.time = 0.0;
+    wave.ray.orig = {0.0, 0.0, 0.0}; wave.ray.dir = {1.0, 0.0, 0.0};
+    rr_ref_shim::tls_beam.active = true; rr_ref_shim::tls_beam.seed = seed;
+    const std::vector<radarays_ros::DirectedWave> waves = radarays_ros::sample_cone_local(wave, width, n_samples, sample_dist, p_in_cone);
+    rr_ref_shim::tls_beam.active = false;
+    for (size_t i = 0; i < waves.size(); i++) {
+        dirs_out[3 * i] = waves[i].ray.dir.x; dirs_out[3 * i + 1] = waves[i].ray.dir.y; dirs_out[3 * i + 2] = waves[i].ray.dir.z;
+    }
+    return (int)waves.size();
 }
 
 } // extern "C"

@@ -21,7 +21,7 @@ extern "C" cudaError_t rr_launch_score(const uint8_t* sim, const uint8_t* real, 
                                        size_t n_goals, unsigned long long* ssd, cudaStream_t st);
 extern "C" cudaError_t rr_launch_peer_exchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch,
                                                const uint8_t* my_gather, uint8_t* d_out, int n_cells, int scroll, int n_poses,
-                                               int32_t* error_flags, cudaStream_t st);
+                                               int32_t* error_flags, int32_t* host_sticky, unsigned long long timeout_ns, cudaStream_t st);
 extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStream_t st);
 extern "C" cudaError_t rr_launch_prep(const RRFrameParams* P, cudaStream_t st);
 extern "C" cudaError_t rr_launch_mat_pairs(const float4* materials, int n_mat, int n_tables, RRMatPair* out, cudaStream_t st);
@@ -61,6 +61,9 @@ struct rr_ctx {
     size_t shard_max_poses = 0;
     uint8_t* shard_base[RR_MAX_PEERS] = {};        /* [flags 256 B | gather buffer 0 | gather buffer 1] of every rank */
     bool shard_connected = false;
+    int32_t* h_peer_timeout = nullptr;             /* mapped pinned flag: rank + 1 of a peer whose columns did not arrive in time (sticky) */
+    int32_t* d_peer_timeout = nullptr;             /* its device alias */
+    unsigned long long peer_timeout_ns = 5000000000ull;   /* RR_PEER_TIMEOUT_MS */
     uint32_t shard_epoch = 0;
     /* rr_gen_radar_images staging */
     float4* d_goal_mat = nullptr; size_t d_goal_mat_cap = 0;
@@ -96,6 +99,7 @@ struct rr_ctx {
         uint32_t* d_tables = nullptr;              /* ctrl | item_start | super_count | item_super: zeroed by ONE memset per launch sequence */
         int2* d_sig_cell = nullptr; float2* d_sig_str = nullptr;
         float4* d_item_xf = nullptr;               /* [max_items][3] item transforms (rr_prep_kernel) */
+        uint8_t* d_stage = nullptr;                /* [max_items][10000 + 15 & ~15] mono8 columns staged by rr_draw_kernel */
     } lanes[kLanes];
     int n_lanes = 2;                               /* rr_set_lanes: 1 = serial launches (per-kernel timing) */
     cudaEvent_t fork_ev = nullptr;
@@ -297,7 +301,7 @@ static void free_lane_scratch(rr_ctx* ctx)
         rr_ctx::Lane& L = ctx->lanes[l];
         cudaFree(L.d_wave_f32); cudaFree(L.d_wave_f64); cudaFree(L.d_wave_mat); cudaFree(L.d_wave_item);
         cudaFree(L.d_sig_cell); cudaFree(L.d_sig_str); cudaFree(L.d_group_base); cudaFree(L.d_first_src);
-        cudaFree(L.d_tables); cudaFree(L.d_item_xf); L.d_item_xf = nullptr;
+        cudaFree(L.d_tables); cudaFree(L.d_item_xf); L.d_item_xf = nullptr; cudaFree(L.d_stage); L.d_stage = nullptr;
         L.d_wave_f32 = nullptr; L.d_wave_f64 = nullptr; L.d_wave_mat = nullptr; L.d_wave_item = nullptr;
         L.d_sig_cell = nullptr; L.d_sig_str = nullptr; L.d_group_base = nullptr; L.d_first_src = nullptr;
         L.d_tables = nullptr;
@@ -390,6 +394,7 @@ void rr_destroy(rr_ctx* ctx)
     cudaFree(ctx->d_mat_pairs); cudaFree(ctx->d_goal_pairs);
     cudaFree(ctx->d_goal_mat); cudaFree(ctx->d_goal_beam); cudaFree(ctx->d_goal_passes); cudaFree(ctx->d_real); cudaFree(ctx->d_ssd);
     cudaFree(ctx->d_weights); cudaFree(ctx->d_noise_decay); cudaFree(ctx->d_beam); cudaFree(ctx->d_tas);
+    if (ctx->h_peer_timeout) cudaFreeHost(ctx->h_peer_timeout);
     for (int p = 0; p < ctx->shard_world; p++) {
         if (!ctx->shard_base[p]) continue;
         if (p == ctx->shard_rank) cudaFree(ctx->shard_base[p]); else cudaIpcCloseMemHandle(ctx->shard_base[p]);
@@ -702,10 +707,11 @@ static int ensure_scratch(rr_ctx* ctx, size_t want_items)
             CK(cudaMalloc((void**)&L.d_wave_item, 2 * slot_cap * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_group_base, 2 * (group_cap + 1) * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_first_src, (group_cap + 1) * sizeof(uint32_t)));
-            CK(cudaMalloc((void**)&L.d_tables, ((3 * RR_MAX_PASSES + 4) + (size_t)(Pn + 1) * ((max_items + 1) + super_stride + item_super_stride)) * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&L.d_tables, ((3 * RR_MAX_PASSES + 4) + (size_t)(Pn + 1) * ((max_items + 1) + super_stride + item_super_stride) + max_items / 8 + 1) * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_sig_cell, (size_t)Pn * wave_cap * sizeof(int2)));
             CK(cudaMalloc((void**)&L.d_sig_str, (size_t)Pn * wave_cap * sizeof(float2)));
             CK(cudaMalloc((void**)&L.d_item_xf, (size_t)max_items * 3 * sizeof(float4)));
+            CK(cudaMalloc((void**)&L.d_stage, (size_t)max_items * 10000));
         }
         ctx->grid = grid; ctx->waves_per_item = wpi; ctx->alloc_passes = Pn; ctx->alloc_samples = S;
         ctx->wave_cap = (uint32_t)wave_cap; ctx->max_items = (uint32_t)max_items;
@@ -743,7 +749,7 @@ static void bind_lane(rr_ctx* ctx, RRFrameParams& P, int lane)
     const rr_ctx::Lane& L = ctx->lanes[lane];
     P.wave_f32 = L.d_wave_f32; P.wave_f64 = L.d_wave_f64; P.wave_mat = L.d_wave_mat; P.wave_item = L.d_wave_item;
     P.group_base = L.d_group_base; P.first_src = L.d_first_src;
-    P.sig_cell = L.d_sig_cell; P.sig_strength = L.d_sig_str; P.item_xf = L.d_item_xf;
+    P.sig_cell = L.d_sig_cell; P.sig_strength = L.d_sig_str; P.item_xf = L.d_item_xf; P.draw_stage = L.d_stage;
 }
 
 /* Host-path options of enqueue(): copy every finished sub-batch to `h_dst` on its lane and mark it with an event. */
@@ -808,6 +814,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
             P.item_start = t; t += (size_t)(Pn + 1) * P.item_stride;
             P.super_count = t; t += (size_t)(Pn + 1) * P.super_stride;
             P.item_super = t; t += (size_t)(Pn + 1) * P.item_super_stride;
+            P.draw_group_done = t; t += items / 8 + 1;
             CK(cudaMemsetAsync(ctx->lanes[lane].d_tables, 0, (size_t)(t - ctx->lanes[lane].d_tables) * sizeof(uint32_t), ls));
         }
         const uint32_t groups0 = (items * (uint32_t)P.n_samples + 31u) / 32u, warps_per_cta = RR_TRACE_BLOCK / 32;
@@ -870,7 +877,10 @@ static int collect_finish(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
     s.kernel_ms = kernel_ms; s.bvh_build_ms = ctx->bvh_build_ms; s.overflow = flags[0];
     if (stats) *stats = s;
     if (flags[1]) return fail(ctx, RR_ERR_OUT_OF_RANGE, "a hit face carries an object id >= n_objects");
-    if (flags[2]) return fail(ctx, RR_ERR_CUDA, "rr_simulate_sharded: a peer did not deliver its columns within 5 s");
+    if (flags[2] || (ctx->h_peer_timeout && *ctx->h_peer_timeout)) {
+        if (ctx->h_peer_timeout) *ctx->h_peer_timeout = 0;
+        return fail(ctx, RR_ERR_PEER_TIMEOUT, "rr_simulate_sharded: a peer did not deliver its columns within %.1f s; the frame is incomplete", ctx->peer_timeout_ns * 1e-9);
+    }
     if (flags[0]) return fail(ctx, RR_ERR_WAVE_OVERFLOW, "wave list overflow (a pass produced more than %u waves per azimuth on average over a launch); raise rr_set_max_waves_per_azimuth", ctx->waves_per_item);
     return RR_OK;
 }
@@ -1152,6 +1162,10 @@ int rr_shard_create(rr_ctx* ctx, int32_t rank, int32_t world, size_t max_poses, 
     static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(rr_ipc_handle), "rr_ipc_handle too small");
     memset(handle_out, 0, sizeof(*handle_out));
     memcpy(handle_out, &h, sizeof(h));
+    CK(cudaHostAlloc((void**)&ctx->h_peer_timeout, sizeof(int32_t), cudaHostAllocMapped));
+    *ctx->h_peer_timeout = 0;
+    CK(cudaHostGetDevicePointer((void**)&ctx->d_peer_timeout, ctx->h_peer_timeout, 0));
+    if (const char* tmo = getenv("RR_PEER_TIMEOUT_MS")) { const long ms = atol(tmo); if (ms > 0) ctx->peer_timeout_ns = (unsigned long long)ms * 1000000ull; }
     ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_max_poses = max_poses;
     ctx->shard_base[rank] = base;
     return RR_OK;
@@ -1184,6 +1198,12 @@ int rr_simulate_sharded(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint6
     if (!ctx->shard_world || (ctx->shard_world > 1 && !ctx->shard_connected)) return fail(ctx, RR_ERR_NOT_READY, "rr_simulate_sharded: rr_shard_create / rr_shard_connect first");
     if (!d_Tsm || !d_out_polar || n_poses == 0 || n_poses > ctx->shard_max_poses)
         return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_simulate_sharded: NULL buffers or n_poses outside [1,%zu]", ctx->shard_max_poses);
+    /* a time-out of an EARLIER frame is reported now (nothing here waits for the device): that frame was incomplete */
+    if (ctx->h_peer_timeout && *ctx->h_peer_timeout) {
+        const int who = *ctx->h_peer_timeout - 1;
+        *ctx->h_peer_timeout = 0;
+        return fail(ctx, RR_ERR_PEER_TIMEOUT, "rr_simulate_sharded: rank %d did not deliver its columns within %.1f s in an earlier call; that frame is incomplete", who, ctx->peer_timeout_ns * 1e-9);
+    }
     const int world = ctx->shard_world, rank = ctx->shard_rank;
     const int base = RR_N_ANGLES / world, extra = RR_N_ANGLES % world;        /* contiguous balanced split (distributed.py) */
     const int az_begin = rank * base + std::min(rank, extra), az_count = base + (rank < extra ? 1 : 0);
@@ -1203,7 +1223,8 @@ int rr_simulate_sharded(rr_ctx* ctx, const rr_pose* d_Tsm, size_t n_poses, uint6
         flags[p] = reinterpret_cast<uint32_t*>(ctx->shard_base[p]);
     }
     if ((rc = enqueue(ctx, P, st, 0, 0))) return rc;
-    CK(rr_launch_peer_exchange(flags, rank, world, epoch, P.peer_out[rank], d_out_polar, P.n_cells, P.scroll_image, (int)n_poses, ctx->d_errflags, st));
+    CK(rr_launch_peer_exchange(flags, rank, world, epoch, P.peer_out[rank], d_out_polar, P.n_cells, P.scroll_image, (int)n_poses, ctx->d_errflags,
+                               ctx->d_peer_timeout, ctx->peer_timeout_ns, st));
     ctx->launches += 3;
     return RR_OK;
 }

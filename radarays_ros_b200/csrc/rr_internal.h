@@ -58,7 +58,7 @@ struct __attribute__((aligned(32))) RRMatPair {
 /* ---- kernel parameter block ---------------------------------------------------------------------*/
 #define RR_MAX_DENOISE 256
 #ifndef RR_BLOCK
-#define RR_BLOCK 128              /* rr_draw_kernel CTA: RR_WARPS warps share one (pose, azimuth) column */
+#define RR_BLOCK 256              /* rr_draw_kernel CTA: RR_WARPS warps share one (pose, azimuth) column (measured: 128 -> 0.636 ms, 256 -> 0.592 ms per 16 poses) */
 #endif
 #define RR_WARPS (RR_BLOCK / 32)
 #ifndef RR_TRACE_BLOCK
@@ -115,6 +115,8 @@ struct RRFrameParams {
     /* output */
     uint8_t* out;                  /* row-major [pose][cell][400] or column-major [pose][az-az_begin][cell] */
     int32_t column_major;
+    uint8_t* draw_stage;           /* [n_items][(n_cells + 15) & ~15] finished mono8 columns, staged for the row-major transposition */
+    uint32_t* draw_group_done;     /* [n_items / 8] columns finished per group of 8 adjacent azimuths (zeroed per launch sequence) */
     /* azimuth-sharded frames over peer memory (rr_simulate_sharded): when n_peers > 0 the draw kernel stores every
      * finished column straight into the gather buffer of EVERY rank (NVLink peer stores), column-major over all 400
      * azimuths: peer_out[p] + ((peer_pose0 + pose) * 400 + azimuth) * n_cells; `out` is not written */

@@ -196,7 +196,7 @@ __device__ __forceinline__ double rr_perlin2(const unsigned char* perm, const do
     const double u = rr_pfade(x), v = rr_pfade(y);
     const int A = perm[X] + Y, B = perm[(X + 1) & 255] + Y;
     const int AA = perm[A & 255], AB = perm[(A + 1) & 255], BA = perm[B & 255], BB = perm[(B + 1) & 255];
-    const double2 c00 = grad[AA], c10 = grad[BA], c01 = grad[AB], c11 = grad[BB];   /* grad[i] = coefficients of perm[i] */
+    const double2 c00 = grad[perm[AA] & 15], c10 = grad[perm[BA] & 15], c01 = grad[perm[AB] & 15], c11 = grad[perm[BB] & 15];   /* grad(p[AA], ...): coefficients by the low 4 hash bits */
     const double xm = x - 1, ym = y - 1;
     const double g00 = c00.x * x + c00.y * y, g10 = c10.x * xm + c10.y * y;
     const double g01 = c01.x * x + c01.y * ym, g11 = c11.x * xm + c11.y * ym;
@@ -619,59 +619,86 @@ __global__ void __launch_bounds__(RR_SCAN_BLOCK) rr_scan_kernel(const RRFramePar
  * The reference adds every return's window of W weighted bins in list order, so a bin's float value depends on the ORDER
  * of the additions that reach it (and on nothing else: bins are independent). The kernel keeps that order per bin without
  * atomics and without replaying the list:
- *   1. count   — every return adds 1 to each 32-bin granule its window overlaps (integer shared-memory atomics, any order);
- *   2. scan    — granule counts -> offsets of per-granule entry lists;
- *   3. fill    — the returns are appended to the lists of their granules IN LIST ORDER: each warp owns a contiguous
- *                quarter of the list (its own cursors, offset by the counts of the quarters before it) and appends 32
- *                returns per step, granule by granule (warp min-reduction picks the next granule, a ballot gives every
- *                lane its rank), so list order = order inside every granule list;
+ *   1. count   — the return list is cut into 32 contiguous pieces; every return adds 1 to the counter (piece, granule)
+ *                of each 32-bin granule its window overlaps (packed 16-bit counters, shared-memory atomics, any order);
+ *   2. scan    — per granule: prefix over the pieces; over the granules: offsets of the per-granule entry lists;
+ *   3. fill    — lane p of warp 0 walks piece p front to back and appends (window start, strength) to the lists of the
+ *                granules it overlaps through its OWN cursors: list order = order inside every granule list, no
+ *                synchronisation, no ranking;
  *   4. add     — a warp takes a granule (dynamic queue), lane <-> bin, the bin's value sits in a REGISTER while the lane
- *                walks the granule's list front to back: one broadcast shared-memory load per entry, the dependent
- *                add chain of the reference and nothing else. A window only engages the lanes of the granules it
- *                overlaps; no return is ever looked at by a warp that has no bin in its window.
+ *                walks the granule's list front to back: one broadcast shared-memory load per entry and the dependent
+ *                add chain of the reference, branch-free. A window only engages the lanes of the granules it overlaps;
+ *                no return is ever looked at by a warp that has no bin in its window.
  * Lists longer than the entry buffer (many passes / wide kernels) are processed in chunks of the return list; the column
  * stays in shared memory between chunks.
  * Epilogue per cell, then the mono8 column goes out as
- *   RR_OUT_CLUSTER  8 CTAs = 8 adjacent azimuths form a thread-block cluster: each CTA reads the 8 byte columns through
- *                   distributed shared memory for its eighth of the cells and stores 8-byte row segments of the
- *                   row-major image (the reference's cv::Mat, Radar.cpp:34) instead of single bytes at stride 400;
- *   RR_OUT_BYTES    the same image with byte stores (shards whose column range is not a multiple of 8, odd scroll);
+ *   RR_OUT_GROUP    row-major image (the reference's cv::Mat, Radar.cpp:34) in 8-byte row segments: the column is staged in
+ *                   global memory (16-byte stores, L2-resident) and the CTA that finishes LAST among 8 adjacent azimuths
+ *                   transposes the 8 columns — nobody waits for anybody;
+ *   RR_OUT_CLUSTER  the same through a thread-block cluster of 8 CTAs reading each other's columns over distributed
+ *                   shared memory (RR_DRAW_USE_CLUSTER=1; measured slower: the 8 CTAs wait for their slowest column);
+ *   RR_OUT_BYTES    byte stores at stride 400 (shards whose column range is not a multiple of 8, odd scroll, debug);
  *   RR_OUT_COLUMNS  column-major shard / NVLink peer stores (16-byte vectors).
  * ---------------------------------------------------------------------------------------------- */
-#ifndef RR_DRAW_ENTRIES
-#define RR_DRAW_ENTRIES 2048          /* (start, strength) entries of a chunk: 16 KB */
+#ifndef RR_DRAW_RETURNS
+#define RR_DRAW_RETURNS 1024          /* returns of a chunk staged in shared memory: 8 KB */
 #endif
-#define RR_DRAW_CLUSTER 8
-enum { RR_OUT_CLUSTER = 0, RR_OUT_BYTES = 1, RR_OUT_COLUMNS = 2 };
+#ifndef RR_DRAW_ENTRIES
+#define RR_DRAW_ENTRIES 3072          /* 16-bit list entries of a chunk: 6 KB (W = 35: <= 3 granules per return) */
+#endif
+#ifndef RR_DRAW_PIECES
+#define RR_DRAW_PIECES 32             /* pieces of the return list = lanes of the filling warp (<= 32) */
+#endif
+#define RR_DRAW_GROUP 8               /* adjacent azimuths per row segment */
+enum { RR_OUT_GROUP = 0, RR_OUT_BYTES = 1, RR_OUT_COLUMNS = 2, RR_OUT_CLUSTER = 3 };
 
+/* 8 byte columns (4 cells each) -> 4 row segments of 8 bytes */
+__device__ __forceinline__ void rr_store_segments(const uint32_t x[RR_DRAW_GROUP], uint8_t* seg, int cell0, int C)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (cell0 + i < C) {
+            const uint32_t sel = (uint32_t)i | ((uint32_t)(4 + i) << 4);
+            const uint32_t lo = __byte_perm(__byte_perm(x[0], x[1], sel), __byte_perm(x[2], x[3], sel), 0x5410);
+            const uint32_t hi = __byte_perm(__byte_perm(x[4], x[5], sel), __byte_perm(x[6], x[7], sel), 0x5410);
+            *reinterpret_cast<uint2*>(seg + (size_t)(cell0 + i) * RR_N_ANGLES) = make_uint2(lo, hi);
+        }
+    }
+}
+
+#ifndef RR_DRAW_MIN_CTAS
+#define RR_DRAW_MIN_CTAS 4
+#endif
 template <bool DEBUG, int OUT>
-__global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P)
+__global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(const RRFrameParams P)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ double s_weights[RR_MAX_DENOISE];         /* float weights widened once (the splat multiplies in double) */
     __shared__ unsigned char s_perm[256];
-    __shared__ double2 s_grad[256];
+    __shared__ double2 s_grad[16];                       /* gradient coefficients by the low 4 hash bits */
     __shared__ float s_red[RR_WARPS];
     __shared__ uint32_t s_begin[RR_MAX_PASSES], s_voff[RR_MAX_PASSES + 1];
-    __shared__ uint32_t s_total, s_next;
+    __shared__ uint32_t s_next, s_nne, s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t item = blockIdx.x;
     const int pose_i = (int)(item / (uint32_t)P.az_count);
     const int az = P.az_begin + (int)(item % (uint32_t)P.az_count);
-    const int C = P.n_cells, C4 = (C + 3) & ~3;
+    const int C = P.n_cells, C16 = (C + 15) & ~15;
     const int n_passes = P.n_passes;
-    const int n_gran = (C + 31) >> 5, G1 = n_gran + 1;           /* <= 313 granules for n_cells <= 10000 */
-    float* s_col = reinterpret_cast<float*>(s_raw);                                    /* [C4] this azimuth's range column   */
-    uint2* s_ent = reinterpret_cast<uint2*>(s_raw + (size_t)C4 * 4);                   /* [RR_DRAW_ENTRIES] (start, strength) */
-    uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_ent);                              /* [C4] mono8 column, after the lists  */
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_raw + (size_t)C4 * 4 + (size_t)RR_DRAW_ENTRIES * 8);   /* [RR_WARPS + 1][G1] */
-    uint32_t* s_off = s_cnt + RR_WARPS * G1;                                           /* [G1] list offsets                   */
+    const int n_gran = (C + 31) >> 5, G1 = (n_gran + 2) & ~1;    /* <= 313 granules for n_cells <= 10000; G1 even */
+    float* s_col = reinterpret_cast<float*>(s_raw);                                    /* [C16] this azimuth's range column     */
+    uint2* s_ret = reinterpret_cast<uint2*>(s_raw + (size_t)C16 * 4);                  /* [RR_DRAW_RETURNS] (cell, strength)    */
+    uint16_t* s_ent = reinterpret_cast<uint16_t*>(s_ret + RR_DRAW_RETURNS);            /* [RR_DRAW_ENTRIES] return indices      */
+    uint8_t* s_bytes = reinterpret_cast<uint8_t*>(s_ret);                              /* [C16] mono8 column, after the lists   */
+    uint16_t* s_tab = s_ent + RR_DRAW_ENTRIES;                                         /* [PIECES][G1] counts -> piece prefixes */
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(s_tab + RR_DRAW_PIECES * G1);        /* [G1] list offsets                     */
+    uint16_t* s_ne = reinterpret_cast<uint16_t*>(s_off + G1);                          /* [G1] granules with a non-empty list   */
 
     for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? (double)P.denoise_weights[i] : 0.0;
-    for (int i = tid; i < 256; i += RR_BLOCK) { s_perm[i] = c_perlin_perm[i]; s_grad[i] = rr_pgrad_coef(c_perlin_perm[i]); }
-    for (int i = tid; i < C4; i += RR_BLOCK) s_col[i] = 0.0f;
+    if (tid < 64) reinterpret_cast<uint32_t*>(s_perm)[tid] = reinterpret_cast<const uint32_t*>(c_perlin_perm)[tid];
+    if (tid < 16) s_grad[tid] = rr_pgrad_coef(tid);
+    for (int i = tid; i < (C16 >> 2); i += RR_BLOCK) reinterpret_cast<float4*>(s_col)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {                                                /* this item's run of every pass list, concatenated */
         const uint32_t S = (uint32_t)P.n_samples;
         uint32_t run = 0;
@@ -693,15 +720,13 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     const int W = P.denoise_on ? P.denoise_width : 1;
     const int mode = P.denoise_on ? P.denoise_mode : 0;
     const int lo_bin = P.denoise_on ? 1 : 0;                       /* glob_id > 0 (:424) only with denoising */
-    const int max_gr = (W + 30) / 32 + 1;                          /* granules one window can overlap */
-    const uint32_t ch_safe = max(16u, ((uint32_t)RR_DRAW_ENTRIES / (2u * (uint32_t)max_gr)) & ~15u);
+    const uint32_t max_gr = (uint32_t)(W + 30) / 32u + 1u;         /* granules one window can overlap */
+    /* a wave carries up to two returns (path, multipath: RadarCPU.cpp:322,358); without record_multi_path the second slot
+     * is never filled and is not even looked at */
+    const uint32_t rpw = P.record_multi_path ? 2u : 1u;
+    /* waves per chunk: their returns fit the staging table and, whatever the windows, their entries fit the lists */
+    const uint32_t ch = max(1u, min((uint32_t)RR_DRAW_RETURNS, (uint32_t)RR_DRAW_ENTRIES / max_gr) / rpw);
 
-    /* virtual slot v of the concatenated list -> (pass, position in the pass list) */
-    auto locate = [&](uint32_t v, int& p, uint32_t& k) {
-        p = 0;
-        while (p + 1 < n_passes && v >= s_voff[p + 1]) p++;
-        k = s_begin[p] + (v - s_voff[p]);
-    };
     /* window of a return: bins [max(st, lo_bin), min(st + W, C)), st = cell - mode; cell < C (:414); very negative cells
      * (no return, time = -inf/NaN) can not reach a bin */
     auto window = [&](int cell, int& g_lo, int& g_hi) -> bool {
@@ -714,124 +739,108 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
     };
 
     float m = 0.0f;                                                /* running max_val (:428-431), per lane */
-    uint32_t c0 = 0, ch = n_slots;                                 /* first attempt: the whole list as one chunk */
-    while (c0 < n_slots) {
-        const uint32_t c1 = min(n_slots, c0 + ch);
-        const uint32_t n_ret = 2u * (c1 - c0);                     /* two return slots per wave */
-        const uint32_t nb = (n_ret + 31u) >> 5;                    /* steps of 32 returns */
-        const uint32_t bpw = (nb + RR_WARPS - 1) / RR_WARPS;       /* steps per warp (contiguous quarters) */
-        for (int i = tid; i < (RR_WARPS + 1) * G1; i += RR_BLOCK) s_cnt[i] = 0u;
+    for (uint32_t c0 = 0; c0 < n_slots; c0 += ch) {
+        const uint32_t n_w = min(ch, n_slots - c0), n_ret = rpw * n_w;
+        const uint32_t plen = (n_ret + RR_DRAW_PIECES - 1) / RR_DRAW_PIECES;      /* returns per piece */
+        /* ---- 0. stage the chunk's returns (coalesced), clear the counters */
+        for (uint32_t e = tid; e < n_ret; e += RR_BLOCK) {
+            const uint32_t v = c0 + (rpw == 2u ? (e >> 1) : e), q = (rpw == 2u) ? (e & 1u) : 0u;
+            int p = 0;
+            while (p + 1 < n_passes && v >= s_voff[p + 1]) p++;
+            const size_t idx = 2 * (size_t)(s_begin[p] + (v - s_voff[p])) + q;
+            const int cell = __ldcs(reinterpret_cast<const int*>(P.sig_cell + (size_t)p * P.wave_cap) + idx);
+            int g_lo, g_hi;
+            uint32_t sv = 0u;
+            if (window(cell, g_lo, g_hi)) sv = __ldcs(reinterpret_cast<const uint32_t*>(P.sig_strength + (size_t)p * P.wave_cap) + idx);
+            s_ret[e] = make_uint2((uint32_t)cell, sv);
+        }
+        for (int i = tid; i < (RR_DRAW_PIECES * G1) / 2; i += RR_BLOCK) reinterpret_cast<uint32_t*>(s_tab)[i] = 0u;
         if (tid == 0) s_next = 0u;
         __syncthreads();
         /* ---- 1. count */
         for (uint32_t e = tid; e < n_ret; e += RR_BLOCK) {
-            int p; uint32_t k;
-            locate(c0 + (e >> 1), p, k);
-            const int cell = __ldg(reinterpret_cast<const int*>(P.sig_cell + (size_t)p * P.wave_cap) + 2 * (size_t)k + (e & 1u));
             int g_lo, g_hi;
-            if (!window(cell, g_lo, g_hi)) continue;
-            uint32_t* cw = s_cnt + ((e >> 5) / bpw) * G1;
-            for (int g = g_lo; g <= g_hi; g++) atomicAdd(&cw[g], 1u);
+            if (!window((int)s_ret[e].x, g_lo, g_hi)) continue;
+            const uint32_t row = (e / plen) * (uint32_t)G1;
+            for (int g = g_lo; g <= g_hi; g++) {
+                const uint32_t i16 = row + (uint32_t)g;
+                atomicAdd(reinterpret_cast<uint32_t*>(s_tab) + (i16 >> 1), 1u << (16u * (i16 & 1u)));
+            }
         }
         __syncthreads();
-        /* ---- 2. scan: list offsets per granule; every warp's cursor starts behind the earlier quarters' entries */
-        if (wid == 0) {
+        /* ---- 2. scan: per granule the prefix over the pieces (a piece's cursor inside the granule's list) and the total ... */
+        for (int g = tid; g < n_gran; g += RR_BLOCK) {
             uint32_t run = 0;
+#pragma unroll 8
+            for (int p = 0; p < RR_DRAW_PIECES; p++) { const uint32_t t = s_tab[p * G1 + g]; s_tab[p * G1 + g] = (uint16_t)run; run += t; }
+            s_off[g] = run;
+        }
+        __syncthreads();
+        /* ... then the list offsets over the granules, and the granules that have a list at all */
+        if (wid == 0) {
+            uint32_t run = 0, nne = 0;
             for (int base = 0; base < n_gran; base += 32) {
                 const int g = base + lane;
-                uint32_t c[RR_WARPS], tot = 0;
-#pragma unroll
-                for (int w = 0; w < RR_WARPS; w++) { c[w] = (g < n_gran) ? s_cnt[w * G1 + g] : 0u; tot += c[w]; }
+                const uint32_t tot = (g < n_gran) ? s_off[g] : 0u;
                 uint32_t incl = tot;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) { const uint32_t nb2 = __shfl_up_sync(RR_FULL, incl, off); if (lane >= off) incl += nb2; }
-                uint32_t o = run + incl - tot;
-                if (g < n_gran) {
-                    s_off[g] = o;
-#pragma unroll
-                    for (int w = 0; w < RR_WARPS; w++) { s_cnt[w * G1 + g] = o; o += c[w]; }
-                }
+                for (int off = 1; off < 32; off <<= 1) { const uint32_t up = __shfl_up_sync(RR_FULL, incl, off); if (lane >= off) incl += up; }
+                const uint32_t ne = __ballot_sync(RR_FULL, tot > 0u);
+                if (g < n_gran) s_off[g] = run + incl - tot;
+                if (tot > 0u) s_ne[nne + __popc(ne & ((1u << lane) - 1u))] = (uint16_t)g;
+                nne += __popc(ne);
                 run += __shfl_sync(RR_FULL, incl, 31);
             }
-            if (lane == 0) { s_off[n_gran] = run; s_total = run; }
+            if (lane == 0) { s_off[n_gran] = run; s_nne = nne; }
         }
         __syncthreads();
-        if (s_total > (uint32_t)RR_DRAW_ENTRIES) {                 /* whole list too long for the buffer: chunks (uniform branch) */
-            __syncthreads();                                       /* everybody has read s_total */
-            ch = ch_safe;                                          /* <= RR_DRAW_ENTRIES entries by construction */
-            continue;
-        }
-        /* ---- 3. fill, in list order */
-        {
-            uint32_t* cur = s_cnt + wid * G1;
-            const uint32_t b_end = min(nb, (uint32_t)(wid + 1) * bpw);
-            for (uint32_t b = (uint32_t)wid * bpw; b < b_end; b++) {
-                const uint32_t e = (b << 5) + (uint32_t)lane;
-                int next = INT32_MAX, g_hi = -1, st = 0;
-                uint32_t sv = 0u;
-                if (e < n_ret) {
-                    int p; uint32_t k;
-                    locate(c0 + (e >> 1), p, k);
-                    const size_t idx = 2 * (size_t)k + (e & 1u);
-                    const int cell = __ldg(reinterpret_cast<const int*>(P.sig_cell + (size_t)p * P.wave_cap) + idx);
-                    int g_lo;
-                    if (window(cell, g_lo, g_hi)) {
-                        next = g_lo; st = cell - mode;
-                        sv = __ldg(reinterpret_cast<const uint32_t*>(P.sig_strength + (size_t)p * P.wave_cap) + idx);
-                    }
-                }
-                for (;;) {
-                    const int g = __reduce_min_sync(RR_FULL, next);
-                    if (g == INT32_MAX) break;
-                    const bool mine = (next == g);
-                    const uint32_t mm = __ballot_sync(RR_FULL, mine);
-                    const uint32_t base = cur[g];
-                    if (mine) {
-                        s_ent[base + __popc(mm & lt_mask)] = make_uint2((uint32_t)st, sv);
-                        next = (g < g_hi) ? g + 1 : INT32_MAX;
-                    }
-                    __syncwarp();
-                    if (lane == 0) cur[g] = base + __popc(mm);
-                    __syncwarp();
-                }
+        /* ---- 3. fill: lane p of warp 0 walks piece p in list order */
+        if (wid == 0 && lane < RR_DRAW_PIECES) {
+            uint16_t* cur = s_tab + lane * G1;
+            const uint32_t pe = min(n_ret, (uint32_t)(lane + 1) * plen);
+            for (uint32_t e = (uint32_t)lane * plen; e < pe; e++) {
+                int g_lo, g_hi;
+                if (!window((int)s_ret[e].x, g_lo, g_hi)) continue;
+                for (int g = g_lo; g <= g_hi; g++) { const uint32_t c = cur[g]; cur[g] = (uint16_t)(c + 1u); s_ent[s_off[g] + c] = (uint16_t)e; }
             }
         }
         __syncthreads();
         /* ---- 4. add: lane <-> bin, value in a register, list front to back */
+        const uint32_t nne = s_nne;
         for (;;) {
-            uint32_t g = 0;
-            if (lane == 0) g = atomicAdd(&s_next, 1u);
-            g = __shfl_sync(RR_FULL, g, 0);
-            if (g >= (uint32_t)n_gran) break;
-            const uint32_t eb = s_off[g], ee = s_off[g + 1];
-            if (eb == ee) continue;
+            uint32_t qi = 0;
+            if (lane == 0) qi = atomicAdd(&s_next, 1u);
+            qi = __shfl_sync(RR_FULL, qi, 0);
+            if (qi >= nne) break;
+            const uint32_t g = s_ne[qi];
+            const uint32_t eb = s_off[g], ee = (g + 1 < (uint32_t)n_gran) ? s_off[g + 1] : s_off[n_gran];
             const int bin = (int)(g << 5) + lane;
             const bool live = (bin >= lo_bin) && (bin < C);
+            /* k = bin - (cell - mode); a lane without a bin gets a k that is outside every window */
+            const int bin_m = live ? bin + mode : -(1 << 24);
             float acc = live ? s_col[bin] : 0.0f;
             if (P.denoise_on) {
+                const uint32_t wmax = (uint32_t)W - 1u;
 #pragma unroll 4
                 for (uint32_t e = eb; e < ee; e++) {
-                    const uint2 en = s_ent[e];
-                    const uint32_t k = (uint32_t)(bin - (int)en.x);
-                    if (live && k < (uint32_t)W) {
-                        acc = (float)((double)acc + (double)__uint_as_float(en.y) * s_weights[k]);
-                        if (acc > m) m = acc;
-                    }
+                    const uint2 rt = s_ret[s_ent[e]];
+                    const uint32_t k = (uint32_t)(bin_m - (int)rt.x);
+                    const float v = (float)((double)acc + (double)__uint_as_float(rt.y) * s_weights[min(k, wmax)]);
+                    acc = (k <= wmax) ? v : acc;                   /* bins outside the window keep their value */
+                    m = fmaxf(m, acc);                             /* == if (acc > m) m = acc, NaN never enters (:428-431) */
                 }
             } else {
                 for (uint32_t e = eb; e < ee; e++) {
-                    const uint2 en = s_ent[e];
-                    if (live && bin == (int)en.x) {
-                        const float sv = __uint_as_float(en.y);
-                        acc = (acc < sv) ? sv : acc;               /* std::max(old, strength), :439 */
-                        if (acc > m) m = acc;
-                    }
+                    const uint2 rt = s_ret[s_ent[e]];
+                    const float sv = __uint_as_float(rt.y);
+                    const float v = (acc < sv) ? sv : acc;         /* std::max(old, strength), :439 */
+                    acc = (live && bin == (int)rt.x) ? v : acc;
+                    m = fmaxf(m, acc);
                 }
             }
             if (live) s_col[bin] = acc;
         }
         __syncthreads();
-        c0 = c1;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) { const float o2 = __shfl_xor_sync(RR_FULL, m, off); if (o2 > m) m = o2; }
@@ -879,34 +888,48 @@ __global__ void __launch_bounds__(RR_BLOCK) rr_draw_kernel(const RRFrameParams P
         if (OUT == RR_OUT_BYTES) out_rows[(size_t)i * RR_N_ANGLES] = px;
         else s_bytes[i] = px;
     }
+    if (OUT != RR_OUT_BYTES && tid < C16 - C) s_bytes[C + tid] = 0;      /* padding of the staged column */
+    /* 8 adjacent azimuths -> 8-byte row segments. For both variants the launcher guarantees: az_count % 8 == 0 (a group
+     * never straddles two poses), (scroll_image + az_begin) % 8 == 0 (segments are aligned and never wrap at column
+     * 400) and an 8-byte aligned image. */
+    if (OUT == RR_OUT_GROUP) {
+        __syncthreads();
+        const uint32_t r = item % RR_DRAW_GROUP, grp = item / RR_DRAW_GROUP;
+        uint4* mine = reinterpret_cast<uint4*>(P.draw_stage + (size_t)item * (size_t)C16);
+        for (int k = tid; k < (C16 >> 4); k += RR_BLOCK) __stcg(mine + k, reinterpret_cast<const uint4*>(s_bytes)[k]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(P.draw_group_done + grp, 1u) == RR_DRAW_GROUP - 1) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {                                               /* the other 7 columns are complete and visible */
+            __threadfence();
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(P.draw_stage + (size_t)grp * RR_DRAW_GROUP * (size_t)C16);
+            uint8_t* seg = out_rows - r;                            /* column of the group's first azimuth */
+            const int n_words = (C + 3) >> 2, stride = C16 >> 2;
+            for (int w = tid; w < n_words; w += RR_BLOCK) {
+                uint32_t x[RR_DRAW_GROUP];
+#pragma unroll
+                for (int j = 0; j < RR_DRAW_GROUP; j++) x[j] = __ldcg(src + (size_t)j * stride + w);
+                rr_store_segments(x, seg, 4 * w, C);
+            }
+        }
+    }
     if (OUT == RR_OUT_CLUSTER) {
-        /* 8 adjacent azimuths -> 8-byte row segments. The launcher guarantees: az_count % 8 == 0 (a cluster never
-         * straddles two poses), (scroll_image + az_begin) % 8 == 0 (segments are aligned and never wrap at column 400)
-         * and an 8-byte aligned image. */
         namespace cg = cooperative_groups;
         cg::cluster_group cl = cg::this_cluster();
         cl.sync();
         const unsigned r = cl.block_rank();
-        const uint32_t* rem[RR_DRAW_CLUSTER];
+        const uint32_t* rem[RR_DRAW_GROUP];
 #pragma unroll
-        for (int j = 0; j < RR_DRAW_CLUSTER; j++) rem[j] = reinterpret_cast<const uint32_t*>(cl.map_shared_rank(s_bytes, j));
-        const int n_words = C4 >> 2, wpr = (n_words + RR_DRAW_CLUSTER - 1) / RR_DRAW_CLUSTER;
+        for (int j = 0; j < RR_DRAW_GROUP; j++) rem[j] = reinterpret_cast<const uint32_t*>(cl.map_shared_rank(s_bytes, j));
+        const int n_words = (C + 3) >> 2, wpr = (n_words + RR_DRAW_GROUP - 1) / RR_DRAW_GROUP;
         const int w_end = min(n_words, (int)(r + 1) * wpr);
-        uint8_t* seg = out_rows - r;                                /* column of the cluster's first azimuth */
+        uint8_t* seg = out_rows - r;
         for (int w = (int)r * wpr + tid; w < w_end; w += RR_BLOCK) {
-            uint32_t x[RR_DRAW_CLUSTER];
+            uint32_t x[RR_DRAW_GROUP];
 #pragma unroll
-            for (int j = 0; j < RR_DRAW_CLUSTER; j++) x[j] = rem[j][w];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int cell = 4 * w + i;
-                if (cell < C) {
-                    const uint32_t sel = (uint32_t)i | ((uint32_t)(4 + i) << 4);
-                    const uint32_t lo = __byte_perm(__byte_perm(x[0], x[1], sel), __byte_perm(x[2], x[3], sel), 0x5410);
-                    const uint32_t hi = __byte_perm(__byte_perm(x[4], x[5], sel), __byte_perm(x[6], x[7], sel), 0x5410);
-                    *reinterpret_cast<uint2*>(seg + (size_t)cell * RR_N_ANGLES) = make_uint2(lo, hi);
-                }
-            }
+            for (int j = 0; j < RR_DRAW_GROUP; j++) x[j] = rem[j][w];
+            rr_store_segments(x, seg, 4 * w, C);
         }
         cl.sync();                                                  /* nobody leaves while its column is still being read */
     }
@@ -987,7 +1010,8 @@ __global__ void rr_peer_signal_kernel(const RRPeerFlags F, int rank, int world, 
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(F.flags[p] + rank), "r"(epoch) : "memory");
 }
 
-__global__ void rr_peer_wait_kernel(const uint32_t* my_flags, int world, uint32_t epoch, int32_t* error_flags)
+__global__ void rr_peer_wait_kernel(const uint32_t* my_flags, int world, uint32_t epoch, int32_t* error_flags,
+                                    volatile int32_t* host_sticky, unsigned long long timeout_ns)
 {
     const int p = threadIdx.x;
     if (p >= world) return;
@@ -998,7 +1022,12 @@ __global__ void rr_peer_wait_kernel(const uint32_t* my_flags, int world, uint32_
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + p) : "memory");
         if ((int32_t)(v - epoch) >= 0) break;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 5000000000ull) { atomicExch(&error_flags[2], 1); break; }     /* 5 s: a peer never arrived */
+        if (t1 - t0 > timeout_ns) {                                /* a peer never arrived: the frame below is incomplete */
+            atomicExch(&error_flags[2], 1);
+            *host_sticky = p + 1;                                  /* zero-copy host flag: stays set until the caller has seen it */
+            __threadfence_system();
+            break;
+        }
         __nanosleep(200);
     }
 }
@@ -1026,12 +1055,12 @@ __global__ void __launch_bounds__(256) rr_gather_transpose_kernel(const uint8_t*
 
 extern "C" cudaError_t rr_launch_peer_exchange(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch,
                                                const uint8_t* my_gather, uint8_t* d_out, int n_cells, int scroll, int n_poses,
-                                               int32_t* error_flags, cudaStream_t st)
+                                               int32_t* error_flags, int32_t* host_sticky, unsigned long long timeout_ns, cudaStream_t st)
 {
     RRPeerFlags F;
     for (int p = 0; p < RR_MAX_PEERS; p++) F.flags[p] = p < world ? peer_flags[p] : nullptr;
     rr_peer_signal_kernel<<<1, 32, 0, st>>>(F, rank, world, epoch);
-    rr_peer_wait_kernel<<<1, 32, 0, st>>>(peer_flags[rank], world, epoch, error_flags);
+    rr_peer_wait_kernel<<<1, 32, 0, st>>>(peer_flags[rank], world, epoch, error_flags, host_sticky, timeout_ns);
     const dim3 grid((unsigned)((n_cells + 31) / 32), (unsigned)((RR_N_ANGLES + 31) / 32), (unsigned)n_poses);
     rr_gather_transpose_kernel<<<grid, 256, 0, st>>>(my_gather, d_out, n_cells, scroll);
     return cudaGetLastError();
@@ -1088,8 +1117,9 @@ extern "C" cudaError_t rr_launch_scan(const RRFrameParams* P, int pass, cudaStre
 
 extern "C" size_t rr_draw_smem_bytes(int n_cells)
 {
-    const size_t c4 = (size_t)((n_cells + 3) & ~3), g1 = (size_t)((n_cells + 31) >> 5) + 1;
-    return c4 * 4 + (size_t)RR_DRAW_ENTRIES * 8 + (size_t)(RR_WARPS + 1) * g1 * 4;
+    const size_t c16 = (size_t)((n_cells + 15) & ~15), g1 = (size_t)((((n_cells + 31) >> 5) + 2) & ~1);
+    const size_t lists = (size_t)RR_DRAW_RETURNS * 8 + (size_t)RR_DRAW_ENTRIES * 2;
+    return c16 * 4 + std::max(lists, c16) + (size_t)RR_DRAW_PIECES * g1 * 2 + g1 * 4 + g1 * 2;
 }
 
 template <bool DEBUG, int OUT>
@@ -1103,7 +1133,7 @@ static cudaError_t rr_draw_launch_one(const RRFrameParams& P, int n_items, size_
     cudaLaunchAttribute at[1];
     if (OUT == RR_OUT_CLUSTER) {
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = RR_DRAW_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = RR_DRAW_GROUP; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
     }
     return cudaLaunchKernelEx(&cfg, rr_draw_kernel<DEBUG, OUT>, P);
@@ -1113,11 +1143,15 @@ extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, cudaS
 {
     const size_t smem = rr_draw_smem_bytes(P->n_cells);
     if (P->n_peers > 0 || P->column_major) return rr_draw_launch_one<false, RR_OUT_COLUMNS>(*P, n_items, smem, st);
-    /* row-major image: 8-byte row segments through a cluster of 8 azimuths when the columns of a cluster are aligned */
-    const bool aligned = (P->az_count % RR_DRAW_CLUSTER == 0) && ((P->scroll_image + P->az_begin) % RR_DRAW_CLUSTER == 0)
-                         && ((reinterpret_cast<size_t>(P->out) & 7) == 0) && !getenv("RR_DRAW_NO_CLUSTER");
-    if (debug) return aligned ? rr_draw_launch_one<true, RR_OUT_CLUSTER>(*P, n_items, smem, st) : rr_draw_launch_one<true, RR_OUT_BYTES>(*P, n_items, smem, st);
-    return aligned ? rr_draw_launch_one<false, RR_OUT_CLUSTER>(*P, n_items, smem, st) : rr_draw_launch_one<false, RR_OUT_BYTES>(*P, n_items, smem, st);
+    if (debug) return rr_draw_launch_one<true, RR_OUT_BYTES>(*P, n_items, smem, st);
+    /* row-major image: 8-byte row segments over groups of 8 adjacent azimuths when the columns of a group are aligned */
+    static const int use_cluster = getenv("RR_DRAW_USE_CLUSTER") ? atoi(getenv("RR_DRAW_USE_CLUSTER")) : 0;
+    static const int use_bytes = getenv("RR_DRAW_BYTES") ? atoi(getenv("RR_DRAW_BYTES")) : 0;
+    const bool aligned = (P->az_count % RR_DRAW_GROUP == 0) && ((P->scroll_image + P->az_begin) % RR_DRAW_GROUP == 0)
+                         && ((reinterpret_cast<size_t>(P->out) & 7) == 0) && !use_bytes;
+    if (!aligned) return rr_draw_launch_one<false, RR_OUT_BYTES>(*P, n_items, smem, st);
+    if (use_cluster) return rr_draw_launch_one<false, RR_OUT_CLUSTER>(*P, n_items, smem, st);
+    return rr_draw_launch_one<false, RR_OUT_GROUP>(*P, n_items, smem, st);
 }
 
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm)

@@ -150,8 +150,13 @@ class RadarB200:
             arr[i] = p if isinstance(p, Pose) else Pose.from_xyz_yaw(*p)
         return arr
 
-    def simulate(self, Tsm, frame_id=None, return_stats=False, out=None):
-        """One frame (Pose), a batch (sequence of Pose) or, with cfg.include_motion, 400 poses per frame.
+    def simulate_motion(self, Tsm_per_azimuth, frame_id=None, return_stats=False, out=None):
+        """include_motion (RadarCPU.cpp:190-196): one pose PER AZIMUTH, n x 400 poses -> n frames."""
+        return self.simulate(Tsm_per_azimuth, frame_id=frame_id, return_stats=return_stats, out=out, motion=True)
+
+    def simulate(self, Tsm, frame_id=None, return_stats=False, out=None, motion=False):
+        """One frame (Pose) or a batch (sequence of Pose); motion=True (or simulate_motion): 400 poses per frame, one
+        per azimuth. The mode is never inferred from the batch length: 400 poses without motion=True are 400 frames.
         Returns uint8 (n_cells, 400) / (n, n_cells, 400); None when Tsm is None (RadarCPU.cpp:129-133).
         `out`: optional caller-owned uint8 array (n, n_cells, 400) to fill instead of a fresh one; when it is
         page-locked (e.g. a torch pin_memory tensor viewed as numpy) the images are copied straight into it."""
@@ -161,7 +166,8 @@ class RadarB200:
             Tsm = self.Tsm_last
         single = isinstance(Tsm, Pose)
         arr = self._poses(Tsm)
-        motion = bool(self.m_cfg.include_motion) and len(arr) % N_ANGLES == 0 and len(arr) >= N_ANGLES
+        if motion and (len(arr) % N_ANGLES != 0 or len(arr) < N_ANGLES):
+            raise ValueError("motion=True needs a multiple of %d poses (one per azimuth), got %d" % (N_ANGLES, len(arr)))
         n = len(arr) // N_ANGLES if motion else len(arr)
         if frame_id is None:
             frame_id = self.frame_counter

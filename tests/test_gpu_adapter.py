@@ -48,4 +48,4 @@ def test_adapter_include_motion(adapter_mod):
     node = adapter_mod.AdapterNode(sc)
     img = node.simulate(cfg, list(per_az), beam_seed=2, noise_seed=3, frame_id=5)
     radar = RadarB200(sc, cfg, beam_seed=2, noise_seed=3)
-    assert np.array_equal(img, radar.simulate(per_az, frame_id=5)) and img.max() > 0
+    assert np.array_equal(img, radar.simulate_motion(per_az, frame_id=5)) and img.max() > 0

@@ -61,3 +61,54 @@ def test_full_size_properties(world):
     assert np.array_equal(assemble_columns(shards, cfg.n_cells, cfg.scroll_image), batch[5])
     st = radar.get_stats()
     assert st.overflow == 0
+
+
+def test_config3_2048_samples_equals_oracle(world, oracle_mod):
+    """BASELINE config 3 at the top of its sweep: urban-5M, 2 passes, 2048 beam samples per azimuth (819 200 pass-0 rays),
+    one full frame against the oracle: casts, hits, returns and every pixel."""
+    sc, cfg, radar = world
+    cfg3 = cfg.copy().update(n_samples=2048, n_reflections=2)
+    radar.updateDynCfg(cfg3)
+    try:
+        img, st = radar.simulate(sc.pose_array()[2], frame_id=11, return_stats=True)
+        o = oracle_mod.OracleScene(sc).simulate(cfg3, radar.getBeamSamples(), sc.pose_array()[2:3], noise_seed=20240310,
+                                                frame_id=11, want_columns=False, records=True, record_capacity=400 * 2048 * 3)
+        assert st.n_casts == len(o["casts"]) and st.n_casts >= 400 * 2048
+        assert st.n_hits == int((o["casts"]["face_id"] >= 0).sum())
+        assert st.n_signals == len(o["signals"])
+        assert np.array_equal(img, o["image"]), "config 3 (2048 samples) frame differs from the oracle"
+    finally:
+        radar.updateDynCfg(cfg)
+
+
+def test_config4_warehouse_1m_equals_oracle(oracle_mod):
+    """BASELINE config 4 at FULL size: warehouse-1M (~1 M triangles), 5 passes, 256 samples, dielectric / metal mix —
+    the wave lists GROW here (glass and plastic wrap split every wave in two). One frame against the oracle bit for bit,
+    then the same frame as 8 azimuth shards (the layout rr_simulate_sharded renders) reassembled."""
+    sc = scenes.warehouse()
+    assert sc.n_tris >= 900_000
+    cfg = RadarModelConfig(**dict(MULRAN_DYNCFG, n_cells=3360, n_samples=256, n_reflections=5, resolution=0.02, include_motion=0))
+    radar = RadarB200(sc, cfg, beam_seed=20240310, noise_seed=20240310)
+    radar.setMaxWavesPerAzimuth(256 * 10)
+    pose = sc.pose_array()[3]
+    img, st = radar.simulate(pose, frame_id=5, return_stats=True)
+    o = oracle_mod.OracleScene(sc).simulate(cfg, radar.getBeamSamples(), sc.pose_array()[3:4], noise_seed=20240310,
+                                            frame_id=5, want_columns=False, records=True, record_capacity=400 * 256 * 40)
+    assert st.overflow == 0
+    assert st.n_casts == len(o["casts"]), "rays*bounces differ"
+    assert st.n_casts > 400 * 256 * 3, "the dielectric splits should make the lists grow"
+    assert st.n_hits == int((o["casts"]["face_id"] >= 0).sum())
+    assert st.n_signals == len(o["signals"])
+    assert np.array_equal(img, o["image"]), "config 4 full-size frame differs from the oracle"
+    dev = torch.device("cuda", 0)
+    p = np.frombuffer((type(pose) * 1)(pose), dtype=np.float32).reshape(1, 7).copy()
+    d_pose = torch.from_numpy(p).to(dev)
+    shards = []
+    for r in range(8):
+        b, c = azimuth_shard(r, 8)
+        d_cols = torch.zeros((c, cfg.n_cells), dtype=torch.uint8, device=dev)
+        radar.simulate_device(d_pose.data_ptr(), 1, d_cols.data_ptr(), frame_id=5, azimuth_begin=b, azimuth_count=c,
+                              column_major=True, stream=torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize()
+        shards.append(d_cols.cpu().numpy())
+    assert np.array_equal(assemble_columns(shards, cfg.n_cells, cfg.scroll_image), img)

@@ -113,6 +113,9 @@ def test_batch_and_motion(oracle_mod):
     x0, y0, z0, yaw0 = sc.poses[0]
     for a in range(400):
         per_az[a] = Pose.from_xyz_yaw(x0 + 0.01 * a, y0, z0, yaw0 + 0.0005 * a)
-    img = radar.simulate(per_az, frame_id=7)
+    img = radar.simulate_motion(per_az, frame_id=7)
+    assert img.shape == (1024, 400)
+    with pytest.raises(ValueError):
+        radar.simulate(per_az[:399], frame_id=7, motion=True)
     o = osc.simulate(cfg2, dirs, per_az, noise_seed=2, frame_id=7)
     assert np.array_equal(img, o["image"])

@@ -82,3 +82,19 @@ def test_reference_bvh_equals_bruteforce(oracle_mod, ref_mod):
     a = rs.simulate(cfg, dirs, sc.pose_array()[:1])["image"]
     b = rs.simulate(cfg, dirs, sc.pose_array()[:1], brute_force=True)["image"]
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dist", [0, 1, 2, 3])
+def test_beam_bundle_equals_the_references_own_sample_cone_local(oracle_mod, ref_mod, dist):
+    """a4: the reference's OWN sample_cone_local (radar_algorithms.cpp:248-294, compiled into oracle/_ref), with its
+    std::mt19937 / uniform / normal distributions fed from the Philox stream in the reference's draw order (pre.h), gives
+    exactly the oracle's bundle. Compared as SETS of float32 directions (bit-exact): oracle and library store the i.i.d.
+    draws along a Morton curve, the reference in draw order."""
+    for n, width, p, seed in [(10, 8.0 * np.pi / 180.0, 0.8, 0), (256, 10.0 * np.pi / 180.0, 0.8, 20240310),
+                              (1000, 0.14, 0.95, 77), (2048, 0.3, 0.5, 2**40 + 3)]:
+        r = ref_mod.sample_cone_local(np.float32(width), n, dist, p, seed)
+        o = oracle_mod.sample_cone(np.float32(width), n, dist, p, seed)
+        assert r.shape == o.shape == (n, 3)
+        rs, os_ = r[np.lexsort(r.T[::-1])], o[np.lexsort(o.T[::-1])]
+        assert np.array_equal(rs.view(np.uint32), os_.view(np.uint32)), "dist %d n %d: bundles differ" % (dist, n)
+        assert np.allclose(np.linalg.norm(r, axis=1), 1.0, atol=1e-6)
