@@ -30,7 +30,8 @@ extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
                                       const float* gs, const float* origins, const float* dirs, size_t n, float tmax,
                                       int32_t* face_ids, float* ranges, cudaStream_t st);
-int rr_bvh_build_device(const RRTriSoup& soup, RRPackedBVH& out, float* build_ms, std::string& err);   /* rr_bvh_build.cu */
+int rr_bvh_build_device(const float* verts, size_t n_verts, const uint32_t* tri_idx, size_t n_tris, const uint32_t* tri_obj,
+                        RRDeviceBVH& out, std::string& err);   /* rr_bvh_build.cu */
 
 static thread_local std::string g_create_error;
 static const size_t kStatusBytes = 8 * sizeof(unsigned long long) + 4 * sizeof(int32_t);
@@ -48,6 +49,7 @@ struct rr_ctx {
     size_t n_nodes = 0, n_tris = 0;
     uint32_t root_ref = 0; float grid_origin[3], grid_scale[3];
     float bvh_build_ms = 0.f;
+    int bvh_depth = 0;
     uint32_t max_object_id = 0;
     /* materials */
     bool have_materials = false;
@@ -425,40 +427,30 @@ int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t*
     if ((n_tris && (!verts || !tri_idx)) || n_tris >= (1u << 28))
         return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: bad arguments (n_tris=%zu, limit 2^28)", n_tris);
     CK(cudaSetDevice(ctx->device));
-    RRTriSoup soup;
-    soup.v0.resize(n_tris); soup.e1.resize(n_tris); soup.e2.resize(n_tris); soup.obj.resize(n_tris);
-    uint32_t max_obj = 0;
-    for (size_t f = 0; f < n_tris; f++) {
-        const uint32_t a = tri_idx[3 * f], b = tri_idx[3 * f + 1], c = tri_idx[3 * f + 2];
-        if (a >= n_verts || b >= n_verts || c >= n_verts)
-            return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: face %zu references a vertex >= n_verts", f);
-        const rr_vec3 A = rr_v3(verts[3 * a], verts[3 * a + 1], verts[3 * a + 2]);
-        const rr_vec3 B = rr_v3(verts[3 * b], verts[3 * b + 1], verts[3 * b + 2]);
-        const rr_vec3 Cc = rr_v3(verts[3 * c], verts[3 * c + 1], verts[3 * c + 2]);
-        soup.v0[f] = A; soup.e1[f] = rr_sub(B, A); soup.e2[f] = rr_sub(Cc, A);
-        soup.obj[f] = tri_object_id ? tri_object_id[f] : 0u;
-        if (soup.obj[f] > max_obj) max_obj = soup.obj[f];
-    }
-    RRPackedBVH bvh;
-    float build_ms = 0.f;
+    /* face -> (v0, e1, e2), SAH tree, depth-first 32-byte nodes and leaf-ordered triangles: all on the device (rr_bvh_build.cu) */
+    RRDeviceBVH bvh;
     std::string berr;
-    const int rc = rr_bvh_build_device(soup, bvh, &build_ms, berr);
-    if (rc != RR_OK) return fail(ctx, rc, "rr_set_mesh: BVH build failed: %s", berr.c_str());
+    const int rc = rr_bvh_build_device(verts, n_verts, tri_idx, n_tris, tri_object_id, bvh, berr);
+    if (rc != RR_OK) {
+        cudaFree(bvh.d_nodes); cudaFree(bvh.d_tris);
+        if (bvh.bad_face >= 0) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: face %lld references a vertex >= n_verts", bvh.bad_face);
+        return fail(ctx, rc, "rr_set_mesh: BVH build failed: %s", berr.c_str());
+    }
     /* the walk postpones at most one subtree per inner node of the current path: a deeper tree would overflow its stack */
-    if (bvh.max_depth > RR_STACK_SIZE)
+    if (bvh.max_depth > RR_STACK_SIZE) {
+        cudaFree(bvh.d_nodes); cudaFree(bvh.d_tris);
         return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: BVH depth %d exceeds the traversal stack (%d entries)", bvh.max_depth, RR_STACK_SIZE);
-    if (getenv("RR_VERBOSE")) fprintf(stderr, "[rr_set_mesh] %zu triangles, %zu nodes, depth %d, build %.1f ms\n", n_tris, bvh.nodes.size(), bvh.max_depth, build_ms);
-    cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris); ctx->d_nodes = nullptr; ctx->d_tris = nullptr;
-    CK(cudaMalloc((void**)&ctx->d_nodes, std::max<size_t>(1, bvh.nodes.size()) * sizeof(RRNode)));
-    CK(cudaMalloc((void**)&ctx->d_tris, std::max<size_t>(1, bvh.tris.size()) * sizeof(float4)));
-    CK(cudaMemcpy(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(RRNode), cudaMemcpyHostToDevice));
-    if (!bvh.tris.empty()) CK(cudaMemcpy(ctx->d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    CK(cudaDeviceSynchronize());                         /* a pageable cudaMemcpy may return before its DMA has landed */
-    ctx->n_nodes = bvh.nodes.size(); ctx->n_tris = n_tris; ctx->root_ref = bvh.root_ref;
+    }
+    if (getenv("RR_VERBOSE")) fprintf(stderr, "[rr_set_mesh] %zu triangles, %zu nodes, depth %d, build %.1f ms\n", n_tris, bvh.n_nodes, bvh.max_depth, bvh.build_ms);
+    ctx->have_mesh = false;
+    cudaFree(ctx->d_nodes); cudaFree(ctx->d_tris);
+    ctx->d_nodes = bvh.d_nodes; ctx->d_tris = bvh.d_tris;
+    ctx->n_nodes = bvh.n_nodes; ctx->n_tris = n_tris; ctx->root_ref = bvh.root_ref;
     memcpy(ctx->grid_origin, bvh.grid_origin, sizeof(ctx->grid_origin));
     memcpy(ctx->grid_scale, bvh.grid_scale, sizeof(ctx->grid_scale));
-    ctx->bvh_build_ms = build_ms;
-    ctx->max_object_id = max_obj;
+    ctx->bvh_build_ms = bvh.build_ms;
+    ctx->max_object_id = bvh.max_object_id;
+    ctx->bvh_depth = bvh.max_depth;
     ctx->have_mesh = true;
     return RR_OK;
 }

@@ -18,6 +18,19 @@ struct RRTriSoup {
     std::vector<uint32_t> obj;
 };
 
+/* result of rr_bvh_build_device: packed nodes and leaf-ordered triangles in device memory (caller frees) */
+struct RRDeviceBVH {
+    RRNode* d_nodes = nullptr;
+    float4* d_tris = nullptr;
+    size_t n_nodes = 0;
+    uint32_t root_ref = 0;
+    float grid_origin[3] = {0, 0, 0}, grid_scale[3] = {1, 1, 1};
+    int max_depth = 0;
+    uint32_t max_object_id = 0;
+    long long bad_face = -1;           /* first face that references a vertex >= n_verts */
+    float build_ms = 0.f;
+};
+
 /* Binned-SAH top-down build on the host (bring-up / fallback for tiny meshes). */
 void rr_bvh_build_host(const RRTriSoup& soup, std::vector<RRBuildNode>& nodes, std::vector<uint32_t>& order);
 

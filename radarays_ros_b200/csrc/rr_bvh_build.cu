@@ -411,54 +411,211 @@ __global__ void k_small(const SmallNode* __restrict__ small, int n_small, uint32
     for (int i = 0; i < n; i++) idx[sn.begin + i] = id[i];
 }
 
+/* ---------------------------------------------------------------- input: vertex / index arrays -> (v0, e1, e2) per face */
+__global__ void k_make_tris(const float* __restrict__ verts, unsigned long long n_verts, const uint32_t* __restrict__ idx,
+                            const uint32_t* __restrict__ obj, int n, float4* tri, uint32_t* status /* [0] first bad face + 1, [1] max object id */)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t my_obj = 0;
+    if (f < n) {
+        const uint32_t a = idx[3 * (size_t)f], b = idx[3 * (size_t)f + 1], c = idx[3 * (size_t)f + 2];
+        if (a >= n_verts || b >= n_verts || c >= n_verts) {
+            atomicMin(&status[0], (uint32_t)f);
+            tri[3 * (size_t)f] = tri[3 * (size_t)f + 1] = tri[3 * (size_t)f + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const rr_vec3 A = rr_v3(verts[3 * (size_t)a], verts[3 * (size_t)a + 1], verts[3 * (size_t)a + 2]);
+            const rr_vec3 B = rr_v3(verts[3 * (size_t)b], verts[3 * (size_t)b + 1], verts[3 * (size_t)b + 2]);
+            const rr_vec3 Cc = rr_v3(verts[3 * (size_t)c], verts[3 * (size_t)c + 1], verts[3 * (size_t)c + 2]);
+            const rr_vec3 e1 = rr_sub(B, A), e2 = rr_sub(Cc, A);          /* the kernels' and the oracle's definition of a face */
+            tri[3 * (size_t)f] = make_float4(A.x, A.y, A.z, 0.f);
+            tri[3 * (size_t)f + 1] = make_float4(e1.x, e1.y, e1.z, 0.f);
+            tri[3 * (size_t)f + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
+        }
+        my_obj = obj ? obj[f] : 0u;
+    }
+    for (int off = 16; off > 0; off >>= 1) my_obj = max(my_obj, __shfl_xor_sync(0xffffffffu, my_obj, off));
+    if ((threadIdx.x & 31) == 0 && my_obj) atomicMax(&status[1], my_obj);
+}
+
+/* ---------------------------------------------------------------- packing on the device: RRBuildNode tree -> 32-byte nodes
+ * in depth-first order (inner nodes only; a child that is a leaf becomes a leaf ref) + leaf-ordered triangles.
+ * parent[]: (parent index << 1) | is_right_child, -1 for the root. */
+__global__ void k_parents(const RRBuildNode* __restrict__ nodes, int n_nodes, int32_t* parent)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    if (i == 0) parent[0] = -1;
+    const RRBuildNode nd = nodes[i];
+    if (nd.left >= 0) { parent[nd.left] = i << 1; parent[nd.right] = (i << 1) | 1; }
+}
+
+/* inner nodes per subtree, bottom-up: every leaf climbs; at a parent the first arrival stops, the second combines */
+__global__ void k_subtree_counts(const RRBuildNode* __restrict__ nodes, int n_nodes, const int32_t* __restrict__ parent,
+                                 uint32_t* flag, volatile uint32_t* cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes || nodes[i].left >= 0) return;
+    int node = i;
+    uint32_t c = 0;
+    for (;;) {
+        cnt[node] = c;
+        const int32_t pp = parent[node];
+        if (pp < 0) break;
+        const int p = pp >> 1;
+        __threadfence();
+        if (atomicAdd(&flag[p], 1u) == 0u) break;
+        __threadfence();
+        c = 1u + cnt[nodes[p].left] + cnt[nodes[p].right];
+        node = p;
+    }
+}
+
+/* depth-first index of every inner node = sum over its path of (1 + inner nodes of the left sibling when coming from the right) */
+__global__ void k_dfs_index(const RRBuildNode* __restrict__ nodes, int n_nodes, const int32_t* __restrict__ parent,
+                            const uint32_t* __restrict__ cnt, uint32_t* packed_idx, int* max_depth)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int depth = 0;
+    if (i < n_nodes && nodes[i].left >= 0) {
+        uint32_t idx = 0;
+        int node = i;
+        depth = 1;
+        for (int32_t pp = parent[node]; pp >= 0; pp = parent[node]) {
+            const int p = pp >> 1;
+            idx += 1u + ((pp & 1) ? cnt[nodes[p].left] : 0u);
+            node = p; depth++;
+        }
+        packed_idx[i] = idx;
+    }
+    for (int off = 16; off > 0; off >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, off));
+    if ((threadIdx.x & 31) == 0 && depth) atomicMax(max_depth, depth);
+}
+
+struct PackGrid { float origin[3], scale[3], pad[3]; };
+
+__device__ __forceinline__ void quant_box(const RRBuildNode& b, const PackGrid& g, uint32_t* w)
+{
+    for (int a = 0; a < 3; a++) {
+        const float o = g.origin[a], s = g.scale[a];
+        const float lo = b.lo[a] - g.pad[a], hi = b.hi[a] + g.pad[a];
+        int ql = (int)floorf((lo - o) / s), qh = (int)ceilf((hi - o) / s);
+        ql = min(max(ql, 0), 65535); qh = min(max(qh, 0), 65535);
+        while (ql > 0 && fmaf((float)ql, s, o) > lo) ql--;          /* conservative under the decode expression */
+        while (qh < 65535 && fmaf((float)qh, s, o) < hi) qh++;
+        ql = max(ql - 1, 0); qh = min(qh + 1, 65535);                /* one cell per side: ray-space rounding (rr_internal.h) */
+        w[a] = (uint32_t)ql | ((uint32_t)qh << 16);
+    }
+}
+
+__global__ void k_pack_nodes(const RRBuildNode* __restrict__ nodes, int n_nodes, const uint32_t* __restrict__ packed_idx,
+                             const PackGrid g, RRNode* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const RRBuildNode nd = nodes[i];
+    if (nd.left < 0) return;
+    const RRBuildNode L = nodes[nd.left], R = nodes[nd.right];
+    RRNode o;
+    quant_box(L, g, &o.w[0]);
+    quant_box(R, g, &o.w[3]);
+    o.c0 = (L.left >= 0) ? packed_idx[nd.left] : (RR_REF_LEAF | ((uint32_t)(L.count - 1) << 28) | (uint32_t)L.first);
+    o.c1 = (R.left >= 0) ? packed_idx[nd.right] : (RR_REF_LEAF | ((uint32_t)(R.count - 1) << 28) | (uint32_t)R.first);
+    out[packed_idx[i]] = o;
+}
+
+__global__ void k_pack_tris(const float4* __restrict__ tri, const uint32_t* __restrict__ order, const uint32_t* __restrict__ obj,
+                            int n, float4* out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t f = order[k];
+    const float4 a = tri[3 * (size_t)f], e1 = tri[3 * (size_t)f + 1], e2 = tri[3 * (size_t)f + 2];
+    out[3 * (size_t)k] = make_float4(a.x, a.y, a.z, rr_u2f(f));
+    out[3 * (size_t)k + 1] = make_float4(e1.x, e1.y, e1.z, rr_u2f(obj ? obj[f] : 0u));
+    out[3 * (size_t)k + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
+}
+
 struct DevBuf {
     std::vector<void*> ptrs;
     template <typename T> cudaError_t alloc(T** p, size_t n) { cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    void release(void* p) { for (auto& q : ptrs) if (q == p) { cudaFree(q); q = nullptr; } }
+    ~DevBuf() { for (void* p : ptrs) if (p) cudaFree(p); }
 };
 
 } // namespace
 
 #define BCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return RR_ERR_CUDA; } } while (0)
 
-int rr_bvh_build_device(const RRTriSoup& soup, RRPackedBVH& out, float* build_ms, std::string& err)
+/* Mesh arrays (host) -> packed BVH + leaf-ordered triangles in DEVICE memory (owned by the caller: cudaFree). Everything
+ * between the upload of the raw arrays and the finished node / triangle arrays runs on the device; the host reads back a
+ * few counters per level, the root bounds and the status words. Meshes of <= RR_SMALL triangles (nothing to parallelise)
+ * are built and packed on the host and uploaded. */
+int rr_bvh_build_device(const float* verts, size_t n_verts, const uint32_t* tri_idx, size_t n_tris, const uint32_t* tri_obj,
+                        RRDeviceBVH& out, std::string& err)
 {
     const auto t0 = std::chrono::steady_clock::now();
-    const int n = (int)soup.v0.size();
-    std::vector<RRBuildNode> nodes;
-    std::vector<uint32_t> order;
-    if (n <= RR_SMALL) {                       /* nothing to parallelise: tiny meshes (config 1's 140 triangles do go through the GPU) */
+    const int n = (int)n_tris;
+    out = RRDeviceBVH();
+    if (n <= RR_SMALL) {
+        RRTriSoup soup;
+        soup.v0.resize(n); soup.e1.resize(n); soup.e2.resize(n); soup.obj.resize(n);
+        for (int f = 0; f < n; f++) {
+            const uint32_t a = tri_idx[3 * f], b = tri_idx[3 * f + 1], c = tri_idx[3 * f + 2];
+            if (a >= n_verts || b >= n_verts || c >= n_verts) { out.bad_face = f; return RR_ERR_INVALID_ARGUMENT; }
+            const rr_vec3 A = rr_v3(verts[3 * a], verts[3 * a + 1], verts[3 * a + 2]);
+            const rr_vec3 B = rr_v3(verts[3 * b], verts[3 * b + 1], verts[3 * b + 2]);
+            const rr_vec3 Cc = rr_v3(verts[3 * c], verts[3 * c + 1], verts[3 * c + 2]);
+            soup.v0[f] = A; soup.e1[f] = rr_sub(B, A); soup.e2[f] = rr_sub(Cc, A);
+            soup.obj[f] = tri_obj ? tri_obj[f] : 0u;
+            out.max_object_id = std::max(out.max_object_id, soup.obj[f]);
+        }
+        std::vector<RRBuildNode> nodes; std::vector<uint32_t> order;
+        RRPackedBVH h;
         rr_bvh_build_host(soup, nodes, order);
-        rr_bvh_pack(soup, nodes, order, out);
-        if (build_ms) *build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        rr_bvh_pack(soup, nodes, order, h);
+        BCK(cudaMalloc((void**)&out.d_nodes, std::max<size_t>(1, h.nodes.size()) * sizeof(RRNode)));
+        BCK(cudaMalloc((void**)&out.d_tris, std::max<size_t>(1, h.tris.size()) * sizeof(float4)));
+        BCK(cudaMemcpy(out.d_nodes, h.nodes.data(), h.nodes.size() * sizeof(RRNode), cudaMemcpyHostToDevice));
+        if (!h.tris.empty()) BCK(cudaMemcpy(out.d_tris, h.tris.data(), h.tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        BCK(cudaDeviceSynchronize());
+        out.n_nodes = h.nodes.size(); out.root_ref = h.root_ref; out.max_depth = h.max_depth;
+        for (int a = 0; a < 3; a++) { out.grid_origin[a] = h.grid_origin[a]; out.grid_scale[a] = h.grid_scale[a]; }
+        out.build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return RR_OK;
     }
     DevBuf db;
-    std::vector<float4> h_tri((size_t)3 * n);
-    for (int i = 0; i < n; i++) {
-        h_tri[3 * (size_t)i] = make_float4(soup.v0[i].x, soup.v0[i].y, soup.v0[i].z, 0.f);
-        h_tri[3 * (size_t)i + 1] = make_float4(soup.e1[i].x, soup.e1[i].y, soup.e1[i].z, 0.f);
-        h_tri[3 * (size_t)i + 2] = make_float4(soup.e2[i].x, soup.e2[i].y, soup.e2[i].z, 0.f);
-    }
+    float* d_verts; uint32_t *d_tidx, *d_obj = nullptr, *d_status;
     float4* d_tri; float *d_plo, *d_phi, *d_pcen; uint32_t *d_idx[2], *d_flag, *d_prefix, *d_bsums, *d_bins, *d_rootb;
     int32_t* d_slot[2]; RRBuildNode* d_nodes; OpenNode* d_open[2]; SmallNode* d_small; int* d_counters;
     const int max_open = n / RR_SMALL + 2;
     const int scan_blocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+    BCK(db.alloc(&d_verts, n_verts * 3)); BCK(db.alloc(&d_tidx, (size_t)3 * n)); BCK(db.alloc(&d_status, (size_t)2));
+    if (tri_obj) BCK(db.alloc(&d_obj, (size_t)n));
     BCK(db.alloc(&d_tri, (size_t)3 * n));
+    BCK(cudaMemcpy(d_verts, verts, n_verts * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    BCK(cudaMemcpy(d_tidx, tri_idx, (size_t)3 * n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (tri_obj) BCK(cudaMemcpy(d_obj, tri_obj, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    const uint32_t status_init[2] = {0xffffffffu, 0u};
+    BCK(cudaMemcpy(d_status, status_init, sizeof(status_init), cudaMemcpyHostToDevice));
+    const int gb = (n + BLD_BLOCK - 1) / BLD_BLOCK;
+    k_make_tris<<<gb, BLD_BLOCK>>>(d_verts, (unsigned long long)n_verts, d_tidx, d_obj, n, d_tri, d_status);
+    BCK(cudaGetLastError());
     BCK(db.alloc(&d_plo, (size_t)3 * n)); BCK(db.alloc(&d_phi, (size_t)3 * n)); BCK(db.alloc(&d_pcen, (size_t)3 * n));
     for (int k = 0; k < 2; k++) { BCK(db.alloc(&d_idx[k], (size_t)n)); BCK(db.alloc(&d_slot[k], (size_t)n)); BCK(db.alloc(&d_open[k], (size_t)max_open)); }
     BCK(db.alloc(&d_flag, (size_t)n)); BCK(db.alloc(&d_prefix, (size_t)n)); BCK(db.alloc(&d_bsums, (size_t)scan_blocks));
     BCK(db.alloc(&d_bins, (size_t)max_open * SLOT_WORDS));
     BCK(db.alloc(&d_nodes, (size_t)2 * n + 2)); BCK(db.alloc(&d_small, (size_t)n)); BCK(db.alloc(&d_counters, (size_t)4)); BCK(db.alloc(&d_rootb, (size_t)12));
-    BCK(cudaMemcpy(d_tri, h_tri.data(), h_tri.size() * sizeof(float4), cudaMemcpyHostToDevice));
     const uint32_t rb_init[12] = {O_POS_INF, O_POS_INF, O_POS_INF, O_NEG_INF, O_NEG_INF, O_NEG_INF, O_POS_INF, O_POS_INF, O_POS_INF, O_NEG_INF, O_NEG_INF, O_NEG_INF};
     BCK(cudaMemcpy(d_rootb, rb_init, sizeof(rb_init), cudaMemcpyHostToDevice));
-    const int gb = (n + BLD_BLOCK - 1) / BLD_BLOCK;
     k_prim_bounds<<<gb, BLD_BLOCK>>>(d_tri, n, d_plo, d_phi, d_pcen, d_rootb);
     k_iota<<<gb, BLD_BLOCK>>>(d_idx[0], d_slot[0], n);
     BCK(cudaGetLastError());
-    uint32_t rb[12];
+    uint32_t rb[12], status[2];
     BCK(cudaMemcpy(rb, d_rootb, sizeof(rb), cudaMemcpyDeviceToHost));
+    BCK(cudaMemcpy(status, d_status, sizeof(status), cudaMemcpyDeviceToHost));
+    out.max_object_id = status[1];
+    if (status[0] != 0xffffffffu) { out.bad_face = (long long)status[0]; return RR_ERR_INVALID_ARGUMENT; }
+    db.release(d_verts); db.release(d_tidx);
     RRBuildNode root;
     OpenNode o0;
     for (int k = 0; k < 3; k++) { root.lo[k] = o2f(rb[k]); root.hi[k] = o2f(rb[3 + k]); o0.clo[k] = o2f(rb[6 + k]); o0.chi[k] = o2f(rb[9 + k]); }
@@ -467,7 +624,7 @@ int rr_bvh_build_device(const RRTriSoup& soup, RRPackedBVH& out, float* build_ms
     o0.child_slot[0] = o0.child_slot[1] = -1; o0.child_node[0] = o0.child_node[1] = -1;
     BCK(cudaMemcpy(d_nodes, &root, sizeof(root), cudaMemcpyHostToDevice));
     BCK(cudaMemcpy(d_open[0], &o0, sizeof(o0), cudaMemcpyHostToDevice));
-    int counters[4] = {1, 0, 0, 0};            /* [0] nodes, [1] next open, [2] small */
+    int counters[4] = {1, 0, 0, 0};            /* [0] nodes, [1] next open, [2] small, [3] max depth */
     BCK(cudaMemcpy(d_counters, counters, sizeof(counters), cudaMemcpyHostToDevice));
 
     int n_open = 1, cur = 0, levels = 0;
@@ -495,16 +652,44 @@ int rr_bvh_build_device(const RRTriSoup& soup, RRPackedBVH& out, float* build_ms
     const int n_small = counters[2];
     if (n_small > 0) k_small<<<(n_small + 63) / 64, 64>>>(d_small, n_small, d_idx[cur], d_plo, d_phi, d_nodes, d_counters);
     BCK(cudaGetLastError());
-    BCK(cudaDeviceSynchronize());
     BCK(cudaMemcpy(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
-    nodes.resize(counters[0]);
-    order.resize(n);
-    BCK(cudaMemcpy(nodes.data(), d_nodes, nodes.size() * sizeof(RRBuildNode), cudaMemcpyDeviceToHost));
-    BCK(cudaMemcpy(order.data(), d_idx[cur], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const int n_bn = counters[0];
     const float dev_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    rr_bvh_pack(soup, nodes, order, out);
-    if (build_ms) *build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (getenv("RR_VERBOSE")) fprintf(stderr, "[rr_bvh] device build: %d tris, %d nodes, %d levels, %d small subtrees, %.1f ms build + pack = %.1f ms\n",
-                                      n, counters[0], levels, n_small, dev_ms, build_ms ? *build_ms : 0.f);
+
+    /* ---- pack on the device. Grid over the padded scene box: pad covers (a) Moeller-Trumbore accepting points a hair
+     * outside a triangle and (b) the rounding of the ray-space plane distances (rr_internal.h); same numbers as rr_bvh_pack */
+    PackGrid g;
+    float ext_max = 0.f;
+    for (int a = 0; a < 3; a++) ext_max = std::max(ext_max, root.hi[a] - root.lo[a]);
+    for (int a = 0; a < 3; a++) {
+        const float lo = root.lo[a], hi = root.hi[a];
+        g.pad[a] = std::max(1e-5f * std::max(1.0f, std::max(std::fabs(lo), std::fabs(hi))), ext_max * 0x1p-20f);
+        const float span = (hi - lo) + 4.f * g.pad[a];
+        g.scale[a] = span / 65527.0f;
+        g.origin[a] = (lo - 2.f * g.pad[a]) - 4.f * g.scale[a];
+        out.grid_origin[a] = g.origin[a]; out.grid_scale[a] = g.scale[a];
+    }
+    /* the binning buffers are free now: reuse them for parent / flag / count / index (4 words per build node) */
+    db.release(d_plo); db.release(d_phi); db.release(d_pcen); db.release(d_bins);
+    int32_t* d_parent; uint32_t *d_done, *d_cnt, *d_pidx;
+    BCK(db.alloc(&d_parent, (size_t)n_bn)); BCK(db.alloc(&d_done, (size_t)n_bn)); BCK(db.alloc(&d_cnt, (size_t)n_bn)); BCK(db.alloc(&d_pidx, (size_t)n_bn));
+    BCK(cudaMemsetAsync(d_done, 0, (size_t)n_bn * sizeof(uint32_t)));
+    const int gn = (n_bn + BLD_BLOCK - 1) / BLD_BLOCK;
+    k_parents<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_parent);
+    k_subtree_counts<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_parent, d_done, d_cnt);
+    k_dfs_index<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_parent, d_cnt, d_pidx, d_counters + 3);
+    BCK(cudaGetLastError());
+    uint32_t n_inner = 0;
+    BCK(cudaMemcpy(&n_inner, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost));       /* inner nodes under (and including) the root */
+    BCK(cudaMalloc((void**)&out.d_nodes, std::max<size_t>(1, n_inner) * sizeof(RRNode)));
+    BCK(cudaMalloc((void**)&out.d_tris, (size_t)3 * n * sizeof(float4)));
+    k_pack_nodes<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_pidx, g, out.d_nodes);
+    k_pack_tris<<<gb, BLD_BLOCK>>>(d_tri, d_idx[cur], d_obj, n, out.d_tris);
+    BCK(cudaGetLastError());
+    BCK(cudaMemcpy(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost));   /* also waits for the pack kernels */
+    out.n_nodes = n_inner; out.root_ref = 0; out.max_depth = counters[3];
+    out.build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("RR_VERBOSE")) fprintf(stderr, "[rr_bvh] device build: %d tris, %d build nodes, %u packed nodes, depth %d, %d levels, %d small subtrees, %.1f ms tree + pack = %.1f ms\n",
+                                      n, n_bn, n_inner, out.max_depth, levels, n_small, dev_ms, out.build_ms);
     return RR_OK;
 }
