@@ -515,9 +515,24 @@ bool load_dae(const std::string& path, Soup& s, std::string& err)
             if (!vs || (id && *id == want)) vs = &v;
         }
     }
+    /* <asset><up_axis>: the file's axes are KEPT by default (what assimp does under AI_CONFIG_IMPORT_COLLADA_IGNORE_UP_DIRECTION,
+     * the setting a ROS map loader needs: map frames are Z-up and Blender exports Z_UP). RR_DAE_UP_AXIS=assimp applies assimp's
+     * default instead, the root transform that turns the document into a Y-up scene (ColladaLoader: Z_UP (x,y,z) -> (x,z,-y),
+     * X_UP (x,y,z) -> (-y,x,z)). */
+    Mat4 root_m = mat_identity();
+    if (const XmlNode* asset = root.child("asset")) if (const XmlNode* up = asset->child("up_axis")) {
+        std::string a = up->text;
+        a.erase(std::remove_if(a.begin(), a.end(), [](unsigned char ch) { return std::isspace(ch); }), a.end());
+        if (a != "X_UP" && a != "Y_UP" && a != "Z_UP") { err = "COLLADA: unknown <up_axis> '" + a + "'"; return false; }
+        const char* mode = getenv("RR_DAE_UP_AXIS");
+        if (mode && std::string(mode) == "assimp") {
+            if (a == "Z_UP") { root_m = Mat4{}; root_m.m[0] = 1; root_m.m[6] = 1; root_m.m[9] = -1; root_m.m[15] = 1; }
+            else if (a == "X_UP") { root_m = Mat4{}; root_m.m[1] = -1; root_m.m[4] = 1; root_m.m[10] = 1; root_m.m[15] = 1; }
+        }
+    }
     uint32_t next_obj = 0;
     if (vs) {
-        for (const XmlNode& n : vs->kids) if (n.name == "node" && !dae_walk(doc, n, mat_identity(), s, next_obj, 0, err)) return false;
+        for (const XmlNode& n : vs->kids) if (n.name == "node" && !dae_walk(doc, n, root_m, s, next_obj, 0, err)) return false;
     }
     if (s.t.empty()) {                                   /* no scene graph: every geometry once, untransformed */
         for (auto& g : doc.geoms) {

@@ -201,3 +201,35 @@ def test_absurd_element_counts_return_a_status_instead_of_aborting(tmp_path, fmt
                   + b"\0" * 64)
     with pytest.raises(RadaRaysError):
         load_mesh(p)
+
+
+GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+
+
+def test_blender_style_collada_with_up_axis(monkeypatch):
+    """A COLLADA document laid out the way Blender's exporter writes it (asset block with <up_axis>Z_UP</up_axis>,
+    effects / materials libraries, interleaved VERTEX / NORMAL / TEXCOORD inputs, one <matrix> per node, the same
+    geometry instanced twice, a camera node): one object id per mesh instance in scene-graph order
+    (config/oru4.yaml:46-65), node matrices applied, the file's Z-up axes kept."""
+    monkeypatch.delenv("RR_DAE_UP_AXIS", raising=False)
+    v, t, o, n_obj = load_mesh(__import__("os").path.join(GOLDEN, "blender_style_scene.dae"))
+    assert n_obj == 3 and len(t) == 2 + 12 + 12
+    assert list(np.unique(o)) == [0, 1, 2] and (o[:2] == 0).all() and (o[2:14] == 1).all() and (o[14:] == 2).all()
+    floor = v[np.unique(t[o == 0])]
+    assert np.allclose(floor.min(0), [-4, -3, 0]) and np.allclose(floor.max(0), [4, 3, 0])
+    c1 = v[np.unique(t[o == 1])]
+    assert np.allclose(c1.min(0), [1.5, 0.5, 0.0]) and np.allclose(c1.max(0), [2.5, 1.5, 1.0])        # scale 0.5, translate (2,1,0.5)
+    c2 = v[np.unique(t[o == 2])]
+    assert np.allclose(c2.min(0), [-3, -2, 0]) and np.allclose(c2.max(0), [-1, 0, 4])                 # rot z 90, z scale 2, translate (-2,-1,2)
+    # assimp's default (without IGNORE_UP_DIRECTION): Z_UP documents are turned into Y-up scenes, (x, y, z) -> (x, z, -y)
+    monkeypatch.setenv("RR_DAE_UP_AXIS", "assimp")
+    v2, t2, o2, _ = load_mesh(__import__("os").path.join(GOLDEN, "blender_style_scene.dae"))
+    assert np.array_equal(t2, t) and np.array_equal(o2, o)
+    assert np.allclose(v2, np.stack([v[:, 0], v[:, 2], -v[:, 1]], 1))
+
+
+def test_meshlab_style_ply_with_extra_properties():
+    """PLY as MeshLab / VCGLIB writes it: normals and colours per vertex, a `flags` property after the index list, a quad."""
+    v, t, o, n_obj = load_mesh(__import__("os").path.join(GOLDEN, "meshlab_style_quad.ply"))
+    assert n_obj == 1 and v.shape == (5, 3) and np.array_equal(v[4], [1, 1, 1.5])
+    assert t.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 4], [0, 4, 3]]

@@ -18,12 +18,12 @@ UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e
 def main():
     rows = [r for r in csv.reader(open(sys.argv[1], errors="replace")) if len(r) > 10]
     h = rows[0]
-    iid, iname, imet, ival, iunit = (h.index(k) for k in ("ID", "Kernel Name", "Metric Name", "Metric Value", "Metric Unit"))
+    iid, iname, imet, ival, iunit, igrid = (h.index(k) for k in ("ID", "Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "Grid Size"))
     launches, order = {}, []
     for r in rows[1:]:
         k = r[iid]
         if k not in launches:
-            launches[k] = {"name": r[iname].split("(")[0].replace("void ", "").split("<")[0]}
+            launches[k] = {"name": r[iname].split("(")[0].replace("void ", "").split("<")[0], "grid": int(r[igrid].strip("()").split(",")[0])}
             order.append(k)
         launches[k][r[imet]] = float(r[ival].replace(",", "")) * UNIT.get(r[iunit], 1.0)
     seqs, cur = [], None
@@ -39,6 +39,16 @@ def main():
            "how": "ncu --clock-control none, tools/profile_configs.sh: second (warm) launch sequence of one 16-pose call per workload, one lane",
            "unit": "bytes per launch sequence of rr_trace_kernel (its per-pass launches summed: dram__bytes_read.sum + dram__bytes_write.sum)",
            "workloads": {}}
+    # a call whose wave lists exceed the per-lane scratch budget runs as several launch sequences: a repetition is
+    # complete when its draw launches cover the 16 x 400 items of the call
+    reps, acc, items = [], [], 0
+    for sq in seqs:
+        acc += sq
+        items += sum(L["grid"] for L in sq if L["name"] == "rr_draw_kernel")
+        if items >= 16 * 400:
+            reps.append(acc)
+            acc, items = [], 0
+    seqs = reps
     si = 0
     print("%-16s %-6s %9s %10s %10s %12s %8s %7s %7s %7s %8s %12s" % ("workload", "kernel", "time_us", "dram_rd_MB", "dram_wr_MB", "warp_inst", "thr/inst", "L1hit%", "L2hit%", "issue%", "warps%", "L2_wr_sect"))
     for lab in labels:

@@ -39,7 +39,7 @@ def run(wl_list, scene):
             torch.cuda.synchronize()
         s = radar.get_stats()
         print(json.dumps({"workload": "config%d_s%d" % (wl.config, wl.cfg.n_samples), "passes": wl.cfg.n_reflections,
-                          "casts": s.n_casts, "sequences": 2}), flush=True)
+                          "casts": s.n_casts, "sequences": 2, "note": "sequences = repetitions of the 16-pose call (a call may run as several launch sequences)"}), flush=True)
     del radar
 
 
