@@ -58,6 +58,7 @@ struct rr_ctx {
     int n_materials = 0, n_objects = 0, air = 0;
     cudaEvent_t upload_ev = nullptr;               /* last setter upload on `stream`; every launch sequence waits for it */
     std::vector<rr_material> materials_host;      /* for rr_get_radar_params (GetRadarParams.srv) */
+    std::vector<int32_t> object_materials_host;
     /* azimuth-sharded frames over peer memory (rr_shard_create / rr_shard_connect / rr_simulate_sharded) */
     int shard_rank = -1, shard_world = 0;
     size_t shard_max_poses = 0;
@@ -481,18 +482,29 @@ int rr_set_materials(rr_ctx* ctx, const rr_material* materials, size_t n_materia
         if (object_materials[o] < 0 || (size_t)object_materials[o] >= n_materials)
             return fail(ctx, RR_ERR_OUT_OF_RANGE, "rr_set_materials: object_materials[%zu] = %d outside [0,%zu)", o, object_materials[o], n_materials);
     CK(cudaSetDevice(ctx->device));
+    /* The node re-reads the parameter server before EVERY frame (radar_simulator.cpp:85,200) and the adapter forwards it:
+     * an unchanged table costs nothing, a changed table of the same shape is uploaded in place (no allocation, no
+     * device synchronisation) — the optimiser's per-goal material updates take this path. */
+    const bool same_shape = ctx->have_materials && (size_t)ctx->n_materials == n_materials && (size_t)ctx->n_objects == n_objects;
+    if (same_shape && ctx->air == material_id_air
+        && memcmp(ctx->materials_host.data(), materials, n_materials * sizeof(rr_material)) == 0
+        && memcmp(ctx->object_materials_host.data(), object_materials, n_objects * sizeof(int32_t)) == 0)
+        return RR_OK;
     std::vector<float4> m(n_materials);
     for (size_t i = 0; i < n_materials; i++) m[i] = make_float4(materials[i].velocity, materials[i].ambient, materials[i].diffuse, materials[i].specular);
-    ctx->have_materials = false;
-    cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials); cudaFree(ctx->d_mat_pairs);      /* cudaFree waits for the device */
-    ctx->d_materials = nullptr; ctx->d_object_materials = nullptr; ctx->d_mat_pairs = nullptr;
-    CK(cudaMalloc((void**)&ctx->d_materials, n_materials * sizeof(float4)));
-    CK(cudaMalloc((void**)&ctx->d_object_materials, n_objects * sizeof(int32_t)));
-    CK(cudaMalloc((void**)&ctx->d_mat_pairs, (n_materials + 1) * sizeof(RRMatPair)));
+    if (!same_shape) {
+        ctx->have_materials = false;
+        cudaFree(ctx->d_materials); cudaFree(ctx->d_object_materials); cudaFree(ctx->d_mat_pairs);      /* cudaFree waits for the device */
+        ctx->d_materials = nullptr; ctx->d_object_materials = nullptr; ctx->d_mat_pairs = nullptr;
+        CK(cudaMalloc((void**)&ctx->d_materials, n_materials * sizeof(float4)));
+        CK(cudaMalloc((void**)&ctx->d_object_materials, n_objects * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&ctx->d_mat_pairs, (n_materials + 1) * sizeof(RRMatPair)));
+    }
     CK(upload(ctx, ctx->d_materials, m.data(), n_materials * sizeof(float4)));
     CK(upload(ctx, ctx->d_object_materials, object_materials, n_objects * sizeof(int32_t)));
     CK(rr_launch_mat_pairs(ctx->d_materials, (int)n_materials, 1, ctx->d_mat_pairs, ctx->stream));
     CK(cudaEventRecord(ctx->upload_ev, ctx->stream));
+    ctx->object_materials_host.assign(object_materials, object_materials + n_objects);
     ctx->n_materials = (int)n_materials; ctx->n_objects = (int)n_objects; ctx->air = material_id_air;
     ctx->materials_host.assign(materials, materials + n_materials);
     ctx->have_materials = true;
@@ -539,9 +551,33 @@ static const char* config_range_error(const rr_config& c, char* buf, size_t n)
     return nullptr;
 }
 
+static bool same_config(const rr_config& a, const rr_config& b)      /* field by field: the struct has padding a C caller need not clear */
+{
+#define RR_EQ(f) (a.f == b.f)
+    return RR_EQ(z_offset) && RR_EQ(range_min) && RR_EQ(range_max) && RR_EQ(beam_width) && RR_EQ(resolution) && RR_EQ(n_cells)
+        && RR_EQ(n_samples) && RR_EQ(beam_sample_dist) && RR_EQ(beam_sample_dist_normal_p_in_cone) && RR_EQ(n_reflections)
+        && RR_EQ(energy_min) && RR_EQ(energy_max) && RR_EQ(signal_max) && RR_EQ(signal_denoising)
+        && RR_EQ(signal_denoising_triangular_width) && RR_EQ(signal_denoising_triangular_mode)
+        && RR_EQ(signal_denoising_gaussian_width) && RR_EQ(signal_denoising_gaussian_mode)
+        && RR_EQ(signal_denoising_mb_width) && RR_EQ(signal_denoising_mb_mode) && RR_EQ(ambient_noise)
+        && RR_EQ(ambient_noise_at_signal_0) && RR_EQ(ambient_noise_at_signal_1) && RR_EQ(ambient_noise_energy_max)
+        && RR_EQ(ambient_noise_energy_min) && RR_EQ(ambient_noise_energy_loss) && RR_EQ(ambient_noise_uniform_max)
+        && RR_EQ(ambient_noise_perlin_scale_low) && RR_EQ(ambient_noise_perlin_scale_high) && RR_EQ(ambient_noise_perlin_p_low)
+        && RR_EQ(scroll_image) && RR_EQ(multipath_threshold) && RR_EQ(record_multi_reflection) && RR_EQ(record_multi_path)
+        && RR_EQ(include_motion);
+#undef RR_EQ
+}
+
 int rr_set_params(rr_ctx* ctx, const rr_model* model, const rr_config* cfg) try
 {
     if (!ctx || !cfg) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_params: cfg is NULL");
+    /* the adapter delivers m_cfg before every frame: an unchanged parameter set is a no-op */
+    if (ctx->have_params && same_config(*cfg, ctx->cfg)) {
+        rr_model mm;
+        if (model) mm = *model;
+        else { mm.beam_width = (float)(cfg->beam_width * M_PI / 180.0); mm.n_samples = (uint32_t)cfg->n_samples; mm.n_reflections = (uint32_t)cfg->n_reflections; }
+        if (mm.beam_width == ctx->model.beam_width && mm.n_samples == ctx->model.n_samples && mm.n_reflections == ctx->model.n_reflections) return RR_OK;
+    }
     /* ---- 1. validate everything; nothing of ctx is modified before the last check has passed */
     char msg[200];
     if (config_range_error(*cfg, msg, sizeof(msg))) return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_params: %s", msg);
