@@ -406,19 +406,22 @@ def main():
     # roofline leg: the same steps with strictly serial launches (one lane), so that the CUDA events the library records
     # on the launch stream around its kernels time each kernel ALONE (in the timed region above two sub-batches of a step
     # overlap on two streams, which is what `value` measures)
-    KR = min(K, 200 if args.config != 5 else 1)
     radar.kernel_times()
     radar.setLanes(1)
     with torch.cuda.stream(stream):
         step(0)
         torch.cuda.synchronize()
         radar.kernel_times()
+        step(0)                                            # how many launch sequences does one step take?
+    torch.cuda.synchronize()
+    seq_per_step = max(1, radar.kernel_times()[2])         # (a call whose lists exceed the lane's scratch budget runs as several)
+    KR = max(1, min(K, 200 // seq_per_step))               # the library remembers 256 launch pairs
+    with torch.cuda.stream(stream):
         for s in range(KR):
             flush.fill_(s & 0xff)
             step((W + s) * PPS)
     torch.cuda.synchronize()
     trace_ms_sum, draw_ms_sum, n_pairs = radar.kernel_times()     # events around the kernels, on the launch stream
-    seq_per_step = max(1, n_pairs // max(KR, 1)) if args.config == 5 else 1
     radar.setLanes(args.lanes)
 
     # single-frame latency of the sharded plane (one pose, all ranks), device time

@@ -68,10 +68,11 @@ class ShardedRadar:
         if p2p:                                   # one-time exchange of the gather buffers' IPC handles
             import torch.distributed as dist
             mine = radar.shardCreate(rank, world, max_poses)
-            handles = [None] * world
-            dist.all_gather_object(handles, mine, group=group)
-            radar.shardConnect(handles)
-            dist.barrier(group=group)
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, mine, group=group)
+                radar.shardConnect(handles)
+                dist.barrier(group=group)
 
     def simulate_p2p(self, pose, frame_id=0):
         """Full frame on every rank through peer memory; returns a torch uint8 tensor [n_cells, 400] on the device."""
