@@ -58,6 +58,19 @@ def gather_frame(local_columns, rank, world, n_cells, scroll_image=0, group=None
     return assemble_columns(shards, n_cells, scroll_image)
 
 
+def assemble_gathered(gathered, counts, scroll_image=0, n_angles=N_ANGLES):
+    """Device-side assembly of an all_gather result: gathered is a torch uint8 tensor [world][n][cmax][n_cells] of
+    column-major shards padded to the largest shard, counts the real shard widths. Returns [n][n_cells][n_angles] in the
+    reference's row-major layout with column (scroll + azimuth) % n_angles (RadarCPU.cpp:457,542)."""
+    import torch
+    cols = torch.cat([gathered[r, :, :counts[r], :] for r in range(len(counts))], dim=1)      # [n][400][C]
+    assert cols.shape[1] == n_angles, "shards do not cover all azimuths"
+    img = cols.permute(0, 2, 1)                                                               # [n][C][400]
+    if scroll_image % n_angles:
+        img = torch.roll(img, shifts=scroll_image % n_angles, dims=2)
+    return img
+
+
 class ShardedRadar:
     """Azimuth-sharded rendering of single frames on `world` GPUs (one process each)."""
 
@@ -106,16 +119,13 @@ class ShardedRadar:
                                        azimuth_count=self.count, column_major=True, stream=stream.cuda_stream)
             if self.count < cmax:
                 mine = torch.cat([mine, torch.zeros((n, cmax - self.count, C), dtype=torch.uint8, device=mine.device)], dim=1)
-            gathered = torch.empty((self.world, n, cmax, C), dtype=torch.uint8, device=mine.device)
+            gathered = torch.empty((self.world * n, cmax, C), dtype=torch.uint8, device=mine.device)   # rank-major concatenation
             if self.world > 1:
                 dist.all_gather_into_tensor(gathered, mine.contiguous(), group=self.group)
             else:
-                gathered[0] = mine
-            cols = torch.cat([gathered[r, :, :counts[r], :] for r in range(self.world)], dim=1)     # [n][400][C]
-            img = cols.permute(0, 2, 1)                                                              # [n][C][400]
-            if cfg.scroll_image % N_ANGLES:
-                img = torch.roll(img, shifts=cfg.scroll_image % N_ANGLES, dims=2)
-            d_out.copy_(img)
+                gathered.copy_(mine)
+            gathered = gathered.view(self.world, n, cmax, C)
+            d_out.copy_(assemble_gathered(gathered, counts, cfg.scroll_image))
         return d_out
 
     def simulate(self, pose, frame_id=0):

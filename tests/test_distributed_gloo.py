@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from radarays_ros_b200.distributed import assemble_columns, azimuth_shard, gather_frame, pose_shard
+from radarays_ros_b200.distributed import assemble_columns, assemble_gathered, azimuth_shard, gather_frame, pose_shard
 
 N_CELLS = 96
 
@@ -33,6 +33,16 @@ def _worker(rank, world, port, scroll, ret):
     local = torch.from_numpy(np.stack([_column(a, N_CELLS) for a in range(begin, begin + count)]))
     img = gather_frame(local, rank, world, N_CELLS, scroll_image=scroll)
     ret[rank] = img
+    # the batched device-side assembly of bench.py --exchange nccl (ShardedRadar.simulate_batch_nccl): padded shards of a
+    # 3-frame batch through all_gather_into_tensor, concatenated / transposed / scrolled as tensors
+    counts = [azimuth_shard(r, world)[1] for r in range(world)]
+    cmax, n = max(counts), 3
+    mine_b = torch.zeros((n, cmax, N_CELLS), dtype=torch.uint8)
+    for f in range(n):
+        mine_b[f, :count] = torch.from_numpy(np.stack([_column(a + 31 * f, N_CELLS) for a in range(begin, begin + count)]))
+    gathered = torch.empty((world * n, cmax, N_CELLS), dtype=torch.uint8)
+    dist.all_gather_into_tensor(gathered, mine_b)
+    ret["batch_%d" % rank] = assemble_gathered(gathered.view(world, n, cmax, N_CELLS), counts, scroll).numpy()
     # pose sharding: every pose is rendered exactly once across the ranks; a MAX all_reduce models the timing rule
     mine = pose_shard(37, rank, world)
     t = torch.tensor([float(len(mine))])
@@ -70,3 +80,7 @@ def test_azimuth_sharded_gather_world2_gloo():
     for r in range(world):
         assert np.array_equal(ret[r], expect)
         assert ret["max_%d" % r] == 19.0          # ceil(37 / 2)
+        assert ret["batch_%d" % r].shape == (3, N_CELLS, 400)
+        for f in range(3):
+            for a in (0, 1, 199, 200, 399):
+                assert np.array_equal(ret["batch_%d" % r][f][:, (a + 3) % 400], _column(a + 31 * f, N_CELLS))
