@@ -941,7 +941,12 @@ static bool host_ptr_is_pinned(const void* p)
 /* Sub-batches of a host-buffer call: the images of a finished sub-batch travel to the host while the next one computes.
  * Measured on the B200 (16 poses, urban-5M): 2 sub-batches 5990 frames/s end to end, 4: 5130, 8: 4240 — launches
  * below 8 poses lose more in the passes' tails than the overlapped copy saves, so: one per lane, 4 from 32 poses on. */
-static int host_split(size_t n_frames) { return (int)std::min<size_t>(n_frames, n_frames >= 32 ? 4 : 2); }
+static int host_split(size_t n_frames)
+{
+    static const int forced = getenv("RR_HOST_SPLIT") ? atoi(getenv("RR_HOST_SPLIT")) : 0;      /* tuning only */
+    if (forced > 0) return (int)std::min<size_t>(n_frames, (size_t)forced);
+    return (int)std::min<size_t>(n_frames, n_frames >= 32 ? 4 : 2);
+}
 
 static int simulate_host(rr_ctx* ctx, const rr_pose* poses, size_t n_frames, int per_az, uint64_t frame_id0,
                          uint8_t* out_polar, rr_stats* stats, int with_stats)

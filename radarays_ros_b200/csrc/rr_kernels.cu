@@ -701,6 +701,7 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
     __shared__ float s_red[RR_WARPS];
     __shared__ uint32_t s_begin[RR_MAX_PASSES], s_voff[RR_MAX_PASSES + 1];
     __shared__ uint32_t s_next, s_nne, s_last;
+    __shared__ uint32_t s_plain;                         /* 1 while every weight and every strength of the chunk is finite and >= 0 */
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t item = blockIdx.x;
@@ -717,7 +718,13 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
     uint32_t* s_off = reinterpret_cast<uint32_t*>(s_tab + RR_DRAW_PIECES * G1);        /* [G1] list offsets                     */
     uint16_t* s_ne = reinterpret_cast<uint16_t*>(s_off + G1);                          /* [G1] granules with a non-empty list   */
 
-    for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) s_weights[i] = (i < P.denoise_width) ? (double)P.denoise_weights[i] : 0.0;
+    bool w_plain = true;
+    for (int i = tid; i < RR_MAX_DENOISE; i += RR_BLOCK) {
+        const float wv = (i < P.denoise_width) ? P.denoise_weights[i] : 0.0f;
+        s_weights[i] = (double)wv;
+        w_plain = w_plain && (wv >= 0.0f) && (wv < INFINITY);
+    }
+    const bool weights_plain = __syncthreads_and(w_plain) != 0;
     if (tid < 64) reinterpret_cast<uint32_t*>(s_perm)[tid] = reinterpret_cast<const uint32_t*>(c_perlin_perm)[tid];
     if (tid < 16) s_grad[tid] = rr_pgrad_coef(tid);
     for (int i = tid; i < (C16 >> 2); i += RR_BLOCK) reinterpret_cast<float4*>(s_col)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -764,7 +771,12 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
     for (uint32_t c0 = 0; c0 < n_slots; c0 += ch) {
         const uint32_t n_w = min(ch, n_slots - c0), n_ret = rpw * n_w;
         const uint32_t plen = (n_ret + RR_DRAW_PIECES - 1) / RR_DRAW_PIECES;      /* returns per piece */
-        /* ---- 0. stage the chunk's returns (coalesced), clear the counters */
+        /* ---- 0. clear the counters */
+        for (int i = tid; i < (RR_DRAW_PIECES * G1) / 2; i += RR_BLOCK) reinterpret_cast<uint32_t*>(s_tab)[i] = 0u;
+        if (tid == 0) { s_next = 0u; s_plain = weights_plain ? 1u : 0u; }
+        __syncthreads();
+        /* ---- 1. stage the chunk's returns in shared memory (coalesced loads) and count them into (piece, granule) */
+        bool plain = true;
         for (uint32_t e = tid; e < n_ret; e += RR_BLOCK) {
             const uint32_t v = c0 + (rpw == 2u ? (e >> 1) : e), q = (rpw == 2u) ? (e & 1u) : 0u;
             int p = 0;
@@ -773,22 +785,19 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
             const int cell = __ldcs(reinterpret_cast<const int*>(P.sig_cell + (size_t)p * P.wave_cap) + idx);
             int g_lo, g_hi;
             uint32_t sv = 0u;
-            if (window(cell, g_lo, g_hi)) sv = __ldcs(reinterpret_cast<const uint32_t*>(P.sig_strength + (size_t)p * P.wave_cap) + idx);
+            if (window(cell, g_lo, g_hi)) {
+                sv = __ldcs(reinterpret_cast<const uint32_t*>(P.sig_strength + (size_t)p * P.wave_cap) + idx);
+                const float svf = __uint_as_float(sv);
+                plain = plain && (svf >= 0.0f) && (svf < INFINITY);
+                const uint32_t row = (e / plen) * (uint32_t)G1;
+                for (int g = g_lo; g <= g_hi; g++) {
+                    const uint32_t i16 = row + (uint32_t)g;
+                    atomicAdd(reinterpret_cast<uint32_t*>(s_tab) + (i16 >> 1), 1u << (16u * (i16 & 1u)));
+                }
+            }
             s_ret[e] = make_uint2((uint32_t)cell, sv);
         }
-        for (int i = tid; i < (RR_DRAW_PIECES * G1) / 2; i += RR_BLOCK) reinterpret_cast<uint32_t*>(s_tab)[i] = 0u;
-        if (tid == 0) s_next = 0u;
-        __syncthreads();
-        /* ---- 1. count */
-        for (uint32_t e = tid; e < n_ret; e += RR_BLOCK) {
-            int g_lo, g_hi;
-            if (!window((int)s_ret[e].x, g_lo, g_hi)) continue;
-            const uint32_t row = (e / plen) * (uint32_t)G1;
-            for (int g = g_lo; g <= g_hi; g++) {
-                const uint32_t i16 = row + (uint32_t)g;
-                atomicAdd(reinterpret_cast<uint32_t*>(s_tab) + (i16 >> 1), 1u << (16u * (i16 & 1u)));
-            }
-        }
+        if (!plain) s_plain = 0u;
         __syncthreads();
         /* ---- 2. scan: per granule the prefix over the pieces (a piece's cursor inside the granule's list) and the total ... */
         for (int g = tid; g < n_gran; g += RR_BLOCK) {
@@ -829,6 +838,7 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
         __syncthreads();
         /* ---- 4. add: lane <-> bin, value in a register, list front to back */
         const uint32_t nne = s_nne;
+        const bool plain_chunk = s_plain != 0u;
         for (;;) {
             uint32_t qi = 0;
             if (lane == 0) qi = atomicAdd(&s_next, 1u);
@@ -841,7 +851,18 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
             /* k = bin - (cell - mode); a lane without a bin gets a k that is outside every window */
             const int bin_m = live ? bin + mode : -(1 << 24);
             float acc = live ? s_col[bin] : 0.0f;
-            if (P.denoise_on) {
+            if (P.denoise_on && plain_chunk) {
+                /* every strength and weight of the chunk is finite and >= 0: a bin outside a return's window may add the
+                 * product with a zero weight instead of being masked ((double)acc + 0.0 == acc exactly, acc is never -0),
+                 * and the column only grows, so its running maximum is its last value */
+#pragma unroll 4
+                for (uint32_t e = eb; e < ee; e++) {
+                    const uint2 rt = s_ret[s_ent[e]];
+                    const uint32_t k = (uint32_t)(bin_m - (int)rt.x);
+                    acc = (float)((double)acc + (double)__uint_as_float(rt.y) * s_weights[min(k, (uint32_t)(RR_MAX_DENOISE - 1))]);
+                }
+                m = fmaxf(m, acc);
+            } else if (P.denoise_on) {
                 const uint32_t wmax = (uint32_t)W - 1u;
 #pragma unroll 4
                 for (uint32_t e = eb; e < ee; e++) {

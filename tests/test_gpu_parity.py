@@ -119,3 +119,21 @@ def test_batch_and_motion(oracle_mod):
         radar.simulate(per_az[:399], frame_id=7, motion=True)
     o = osc.simulate(cfg2, dirs, per_az, noise_seed=2, frame_id=7)
     assert np.array_equal(img, o["image"])
+
+
+def test_negative_strengths_take_the_masked_accumulation_path(oracle_mod):
+    """The draw kernel adds zero-weight products outside a return's window only while every strength and weight of the
+    chunk is finite and >= 0; a material with a negative constant term (negative returns: columns that shrink, a running
+    max that is not the last value) must take the masked path and still equal the reference's loop bit for bit."""
+    sc = scenes.box_room_cylinder()
+    sc.materials = [sc.materials[0], (0.0, -0.75, 0.5, 4.0), (0.03, 1.0, 0.0, 100.0)]      # walls: negative ambient term
+    cfg = RadarModelConfig(n_reflections=3, ambient_noise=2, include_motion=0, n_samples=40, signal_denoising=1)
+    radar = RadarB200(sc, cfg, beam_seed=8, noise_seed=9)
+    radar.setMaxWavesPerAzimuth(cfg.n_samples * 16)
+    dirs = radar.getBeamSamples()
+    o = oracle_mod.OracleScene(sc).simulate(cfg, dirs, sc.pose_array()[:1], noise_seed=9, frame_id=2, records=True,
+                                            record_capacity=400 * 40 * 16)
+    g = radar.debug_trace(sc.pose_array()[0], frame_id=2, capacity=400 * 40 * 16)
+    assert (o["signals"]["strength"] < 0).any() and (o["signals"]["strength"] > 0).any()
+    _compare_records(g, o)
+    assert np.array_equal(radar.simulate(sc.pose_array()[0], frame_id=2), o["image"])
