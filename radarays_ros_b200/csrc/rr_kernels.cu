@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(RR_SCAN_BLOCK) rr_scan_kernel(const RRFramePar
 #define RR_DRAW_ENTRIES 3072          /* 16-bit list entries of a chunk: 6 KB (W = 35: <= 3 granules per return) */
 #endif
 #ifndef RR_DRAW_PIECES
-#define RR_DRAW_PIECES 32             /* pieces of the return list = lanes of the filling warp (<= 32) */
+#define RR_DRAW_PIECES 32             /* pieces of the return list = threads that fill the lists (<= RR_BLOCK) */
 #endif
 #define RR_DRAW_GROUP 8               /* adjacent azimuths per row segment */
 enum { RR_OUT_GROUP = 0, RR_OUT_BYTES = 1, RR_OUT_COLUMNS = 2, RR_OUT_CLUSTER = 3 };
@@ -826,10 +826,10 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
         }
         __syncthreads();
         /* ---- 3. fill: lane p of warp 0 walks piece p in list order */
-        if (wid == 0 && lane < RR_DRAW_PIECES) {
-            uint16_t* cur = s_tab + lane * G1;
-            const uint32_t pe = min(n_ret, (uint32_t)(lane + 1) * plen);
-            for (uint32_t e = (uint32_t)lane * plen; e < pe; e++) {
+        if (tid < RR_DRAW_PIECES) {
+            uint16_t* cur = s_tab + tid * G1;
+            const uint32_t pe = min(n_ret, (uint32_t)(tid + 1) * plen);
+            for (uint32_t e = (uint32_t)tid * plen; e < pe; e++) {
                 int g_lo, g_hi;
                 if (!window((int)s_ret[e].x, g_lo, g_hi)) continue;
                 for (int g = g_lo; g <= g_hi; g++) { const uint32_t c = cur[g]; cur[g] = (uint16_t)(c + 1u); s_ent[s_off[g] + c] = (uint16_t)e; }

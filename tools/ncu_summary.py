@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Text summary of one `ncu --set full --import-source on` capture: headline metrics, stall reasons, hottest source lines.
-usage: python tools/ncu_summary.py gpurun_out/X.ncu-rep > profiles/X_summary.txt"""
+usage: python tools/ncu_summary.py gpurun_out/X.ncu-rep [top_n [launch_index]] > profiles/X_summary.txt"""
 import csv
 import io
 import subprocess
@@ -27,8 +27,9 @@ def ncu(args):
 def main():
     rep = sys.argv[1]
     topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    which = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # which captured launch of the report (0-based)
     rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
-    h, units, r = rows[0], rows[1], rows[2]
+    h, units, r = rows[0], rows[1], rows[2 + which]
     print("# %s" % rep.split("/")[-1])
     print("kernel: %s" % r[h.index("Kernel Name")])
     for w in WANT:
@@ -46,7 +47,7 @@ def main():
     print("\nwarp stall reasons (pc samples):")
     for v, n in sorted(stalls, reverse=True)[:10]:
         print("  %5.1f%%  %s" % (100 * v / tot, n))
-    src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"]))))
+    src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--launch-skip", str(which), "--launch-count", "1"]))))
     cur, hdr, ci, agg = None, None, None, {}
     for row in src:
         if len(row) == 2 and row[0] == "File Path":
