@@ -134,3 +134,21 @@ def test_cpp_example_program(tmp_path):
     radar.loadParams([(0.3, 1.0, 0.0, 1.0), (0.0, 1.0, 0.0, 3000.0)], [1], 0)
     want = radar.simulate(Pose.from_xyz_yaw(x, y, z, yaw), frame_id=0)
     assert np.array_equal(img, want) and img.max() > 0
+
+
+@pytest.mark.parametrize("n_cells", [257, 1001, 3360, 10000])
+def test_row_major_output_paths_equal_the_oracle(oracle_mod, n_cells):
+    """The image leaves the draw kernel either as 8-byte row segments (groups of 8 adjacent azimuths, the last CTA of a
+    group transposes the staged columns; needs scroll % 8 == 0) or as single bytes (any other scroll): both against the
+    oracle for column lengths that are not multiples of 4 / 16 and for the 10000-cell maximum, on a pose batch."""
+    sc = scenes.box_room_cylinder()
+    for scroll in (0, 8, 392, 3):
+        cfg = RadarModelConfig(n_reflections=2, include_motion=0, n_cells=n_cells, resolution=30.0 / n_cells, n_samples=12,
+                               ambient_noise=2, scroll_image=scroll)
+        radar = RadarB200(sc, cfg, beam_seed=4, noise_seed=5)
+        poses = sc.pose_array(3)
+        imgs = radar.simulate(poses, frame_id=60)
+        osc = oracle_mod.OracleScene(sc)
+        for i in range(3):
+            o = osc.simulate(cfg, radar.getBeamSamples(), poses[i:i + 1], noise_seed=5, frame_id=60 + i)
+            assert np.array_equal(imgs[i], o["image"]), "n_cells %d scroll %d pose %d" % (n_cells, scroll, i)
