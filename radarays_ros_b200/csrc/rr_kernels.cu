@@ -209,16 +209,26 @@ __device__ __forceinline__ double2 rr_pgrad_coef(int h)
 }
 __device__ __forceinline__ double rr_pfade(double t) { return t * t * t * (t * (t * 6 - 15) + 10); }
 __device__ __forceinline__ double rr_plerp(double t, double a, double b) { return a + t * (b - a); }
-__device__ __forceinline__ double rr_perlin2(const unsigned char* perm, const double2* grad, double sx, double sy)
+/* the part of the evaluation that depends on the second coordinate only: constant along a range column */
+struct RRPerlinRow { int Y; double y, ym, v; };
+__device__ __forceinline__ RRPerlinRow rr_perlin_row(double sy)
 {
-    const double fx = floor(sx), fy = floor(sy);
-    const int X = ((int)fx) & 255, Y = ((int)fy) & 255;
-    const double x = sx - fx, y = sy - fy;
-    const double u = rr_pfade(x), v = rr_pfade(y);
+    RRPerlinRow r;
+    const double fy = floor(sy);
+    r.Y = ((int)fy) & 255;
+    r.y = sy - fy; r.ym = r.y - 1; r.v = rr_pfade(r.y);
+    return r;
+}
+__device__ __forceinline__ double rr_perlin2(const unsigned char* perm, const double2* grad, double sx, const RRPerlinRow row)
+{
+    const double fx = floor(sx);
+    const int X = ((int)fx) & 255, Y = row.Y;
+    const double x = sx - fx, y = row.y;
+    const double u = rr_pfade(x), v = row.v;
     const int A = perm[X] + Y, B = perm[(X + 1) & 255] + Y;
     const int AA = perm[A & 255], AB = perm[(A + 1) & 255], BA = perm[B & 255], BB = perm[(B + 1) & 255];
     const double2 c00 = grad[perm[AA] & 15], c10 = grad[perm[BA] & 15], c01 = grad[perm[AB] & 15], c11 = grad[perm[BB] & 15];   /* grad(p[AA], ...): coefficients by the low 4 hash bits */
-    const double xm = x - 1, ym = y - 1;
+    const double xm = x - 1, ym = row.ym;
     const double g00 = c00.x * x + c00.y * y, g10 = c10.x * xm + c10.y * y;
     const double g01 = c01.x * x + c01.y * ym, g11 = c11.x * xm + c11.y * ym;
     const double lower = rr_plerp(v, rr_plerp(u, g00, g10), rr_plerp(u, g01, g11));
@@ -828,11 +838,23 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
         /* ---- 3. fill: thread p walks piece p in list order */
         if (tid < RR_DRAW_PIECES) {
             uint16_t* cur = s_tab + tid * G1;
-            const uint32_t pe = min(n_ret, (uint32_t)(tid + 1) * plen);
-            for (uint32_t e = (uint32_t)tid * plen; e < pe; e++) {
+            const uint32_t pb = (uint32_t)tid * plen, pe = min(n_ret, (uint32_t)(tid + 1) * plen);
+            int next_cell = (pb < pe) ? (int)s_ret[pb].x : 0;      /* the next return's cell is loaded before this one's stores */
+            for (uint32_t e = pb; e < pe; e++) {
+                const int cell = next_cell;
+                if (e + 1 < pe) next_cell = (int)s_ret[e + 1].x;
                 int g_lo, g_hi;
-                if (!window((int)s_ret[e].x, g_lo, g_hi)) continue;
-                for (int g = g_lo; g <= g_hi; g++) { const uint32_t c = cur[g]; cur[g] = (uint16_t)(c + 1u); s_ent[s_off[g] + c] = (uint16_t)e; }
+                if (!window(cell, g_lo, g_hi)) continue;
+                if (g_hi - g_lo <= 2) {                            /* up to 3 granules (W <= 65): the three cursor chains side by side */
+                    const bool h1 = g_hi > g_lo, h2 = g_hi > g_lo + 1;
+                    const uint32_t c0 = cur[g_lo], c1 = h1 ? cur[g_lo + 1] : 0u, c2 = h2 ? cur[g_lo + 2] : 0u;
+                    const uint32_t o0 = s_off[g_lo], o1 = h1 ? s_off[g_lo + 1] : 0u, o2 = h2 ? s_off[g_lo + 2] : 0u;
+                    cur[g_lo] = (uint16_t)(c0 + 1u); s_ent[o0 + c0] = (uint16_t)e;
+                    if (h1) { cur[g_lo + 1] = (uint16_t)(c1 + 1u); s_ent[o1 + c1] = (uint16_t)e; }
+                    if (h2) { cur[g_lo + 2] = (uint16_t)(c2 + 1u); s_ent[o2 + c2] = (uint16_t)e; }
+                } else {
+                    for (int g = g_lo; g <= g_hi; g++) { const uint32_t c = cur[g]; cur[g] = (uint16_t)(c + 1u); s_ent[s_off[g] + c] = (uint16_t)e; }
+                }
             }
         }
         __syncthreads();
@@ -904,7 +926,7 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
     const double random_begin = (P.ambient_noise == 2)
         ? (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 0u) * 1000.0 : 0.0;
     const float out_scale = (float)(P.signal_max / (double)max_val);
-    const double ycoord1 = (double)col * 0.05, ycoord2 = (double)col * 0.2;
+    const RRPerlinRow row1 = rr_perlin_row((double)col * 0.05), row2 = rr_perlin_row((double)col * 0.2);
     uint8_t* out_rows = P.out + (size_t)pose_i * (size_t)C * RR_N_ANGLES + col;
     for (int i = tid; i < C; i += RR_BLOCK) {
         float v = s_col[i] * P.energy_max_f;
@@ -913,8 +935,8 @@ __global__ void __launch_bounds__(RR_BLOCK, RR_DRAW_MIN_CTAS) rr_draw_kernel(con
             if (P.ambient_noise == 1) {
                 p = (double)rr_noise_u01(P.noise_seed, frame_id, (uint32_t)az, 1u + (uint32_t)i);
             } else if (P.ambient_noise == 2) {
-                const double p1 = rr_perlin2(s_perm, s_grad, random_begin + (double)i * 0.05, ycoord1);
-                const double p2 = rr_perlin2(s_perm, s_grad, random_begin + (double)i * 0.2, ycoord2);
+                const double p1 = rr_perlin2(s_perm, s_grad, random_begin + (double)i * 0.05, row1);
+                const double p2 = rr_perlin2(s_perm, s_grad, random_begin + (double)i * 0.2, row2);
                 p = 0.9 * p1 + 0.1 * p2;
             }
             const float sn = (float)(1.0 - (double)((v - 0.0f) / signal_amp));
