@@ -27,6 +27,9 @@ extern "C" cudaError_t rr_launch_prep(const RRFrameParams* P, cudaStream_t st);
 extern "C" cudaError_t rr_launch_mat_pairs(const float4* materials, int n_mat, int n_tables, RRMatPair* out, cudaStream_t st);
 extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
+extern "C" cudaError_t rr_split_occupancy(int* walk_blocks_per_sm, int* shade_blocks_per_sm);
+extern "C" cudaError_t rr_launch_walk(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats);
+extern "C" cudaError_t rr_launch_shade(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
                                       const float* gs, const float* origins, const float* dirs, size_t n, float tmax,
                                       int32_t* face_ids, float* ranges, cudaStream_t st);
@@ -43,6 +46,8 @@ struct rr_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = 0;
     int trace_ctas_per_sm = 0;
+    int walk_ctas_per_sm = 0, shade_ctas_per_sm = 0;
+    int split_pass = 0;                            /* 1: every pass runs as rr_walk_kernel + rr_shade_kernel instead of rr_trace_kernel */
     /* scene */
     bool have_mesh = false;
     RRNode* d_nodes = nullptr; float4* d_tris = nullptr;
@@ -101,12 +106,16 @@ struct rr_ctx {
         uint32_t* d_group_base = nullptr; uint32_t* d_first_src = nullptr;
         uint32_t* d_tables = nullptr;              /* ctrl | item_start | super_count | item_super: zeroed by ONE memset per launch sequence */
         int2* d_sig_cell = nullptr; float2* d_sig_str = nullptr;
+        int2* d_hit_rec = nullptr;                 /* [wave_cap] cast results handed from rr_walk_kernel to rr_shade_kernel */
         float4* d_item_xf = nullptr;               /* [max_items][3] item transforms (rr_prep_kernel) */
         uint8_t* d_stage = nullptr;                /* [max_items][10000 + 15 & ~15] mono8 columns staged by rr_draw_kernel */
     } lanes[kLanes];
     int n_lanes = 2;                               /* rr_set_lanes: 1 = serial launches (per-kernel timing) */
     cudaEvent_t fork_ev = nullptr;
     std::vector<cudaEvent_t> sub_ev;               /* one per sub-batch of the host path (copy finished) */
+    std::vector<cudaEvent_t> drawn_ev;             /* one per sub-batch of the host path (image finished on its lane) */
+    cudaStream_t copy_stream = nullptr;            /* device->host image copies of the host path: a lane never waits for a copy */
+    cudaEvent_t copy_done = nullptr;
     int grid = 0;
     uint32_t waves_per_item = 0, wave_cap = 0, max_items = 0;   /* list capacity: per item, per lane; items per launch sequence */
     uint32_t super_stride = 0, item_super_stride = 0;
@@ -303,6 +312,7 @@ static void free_lane_scratch(rr_ctx* ctx)
     for (int l = 0; l < rr_ctx::kLanes; l++) {
         rr_ctx::Lane& L = ctx->lanes[l];
         cudaFree(L.d_wave_f32); cudaFree(L.d_wave_f64); cudaFree(L.d_wave_mat); cudaFree(L.d_wave_item);
+        cudaFree(L.d_hit_rec); L.d_hit_rec = nullptr;
         cudaFree(L.d_sig_cell); cudaFree(L.d_sig_str); cudaFree(L.d_group_base); cudaFree(L.d_first_src);
         cudaFree(L.d_tables); cudaFree(L.d_item_xf); L.d_item_xf = nullptr; cudaFree(L.d_stage); L.d_stage = nullptr;
         L.d_wave_f32 = nullptr; L.d_wave_f64 = nullptr; L.d_wave_mat = nullptr; L.d_wave_item = nullptr;
@@ -367,6 +377,8 @@ int rr_create(rr_ctx** out, int device_id) try
         if ((e = cudaEventCreateWithFlags(&ctx->lanes[l].done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
     if ((e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->upload_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     /* counters[8] (u64) | error_flags[4] (i32): one allocation, one memset per call, one read-back */
     if ((e = cudaMalloc((void**)&ctx->d_counters, kStatusBytes)) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -408,6 +420,9 @@ void rr_destroy(rr_ctx* ctx)
         if (ctx->lanes[l].stream) cudaStreamDestroy(ctx->lanes[l].stream);
     }
     for (cudaEvent_t ev : ctx->sub_ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->drawn_ev) cudaEventDestroy(ev);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);
     cudaFree(ctx->d_counters); if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -707,7 +722,12 @@ static int ready(rr_ctx* ctx)
  * items per launch sequence (each lane bounded to ~4 GB of the 180 GB; larger batches run as several sequences). */
 static int ensure_scratch(rr_ctx* ctx, size_t want_items)
 {
-    if (ctx->trace_ctas_per_sm < 1) CK(rr_trace_occupancy(&ctx->trace_ctas_per_sm));   /* per context = per device */
+    if (ctx->trace_ctas_per_sm < 1) {                  /* per context = per device */
+        CK(rr_trace_occupancy(&ctx->trace_ctas_per_sm));
+        CK(rr_split_occupancy(&ctx->walk_ctas_per_sm, &ctx->shade_ctas_per_sm));
+        if (getenv("RR_PASS_SPLIT")) ctx->split_pass = atoi(getenv("RR_PASS_SPLIT")) ? 1 : 0;
+        if (ctx->walk_ctas_per_sm < 1 || ctx->shade_ctas_per_sm < 1) ctx->split_pass = 0;
+    }
     const int per_sm = ctx->trace_ctas_per_sm;
     if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "trace kernel does not fit on an SM");
     const int grid = ctx->num_sms * per_sm;
@@ -738,6 +758,7 @@ static int ensure_scratch(rr_ctx* ctx, size_t want_items)
             CK(cudaMalloc((void**)&L.d_tables, ((3 * RR_MAX_PASSES + 4) + (size_t)(Pn + 1) * ((max_items + 1) + super_stride + item_super_stride) + max_items / 8 + 1) * sizeof(uint32_t)));
             CK(cudaMalloc((void**)&L.d_sig_cell, (size_t)Pn * wave_cap * sizeof(int2)));
             CK(cudaMalloc((void**)&L.d_sig_str, (size_t)Pn * wave_cap * sizeof(float2)));
+            CK(cudaMalloc((void**)&L.d_hit_rec, wave_cap * sizeof(int2)));
             CK(cudaMalloc((void**)&L.d_item_xf, (size_t)max_items * 3 * sizeof(float4)));
             CK(cudaMalloc((void**)&L.d_stage, (size_t)max_items * 10000));
         }
@@ -778,6 +799,7 @@ static void bind_lane(rr_ctx* ctx, RRFrameParams& P, int lane)
     P.wave_f32 = L.d_wave_f32; P.wave_f64 = L.d_wave_f64; P.wave_mat = L.d_wave_mat; P.wave_item = L.d_wave_item;
     P.group_base = L.d_group_base; P.first_src = L.d_first_src;
     P.sig_cell = L.d_sig_cell; P.sig_strength = L.d_sig_str; P.item_xf = L.d_item_xf; P.draw_stage = L.d_stage;
+    P.hit_rec = L.d_hit_rec;
 }
 
 /* Host-path options of enqueue(): copy every finished sub-batch to `h_dst` on its lane and mark it with an event. */
@@ -805,22 +827,34 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
     const RRMatPair* pairs0 = P.mat_pairs;
     const size_t out_stride = P.column_major ? (size_t)P.az_count * P.n_cells : (size_t)P.n_cells * RR_N_ANGLES;
     const int Pn = P.n_passes;
-    const int n_sub = (n_total + poses_per_launch - 1) / poses_per_launch;
+    /* sub-batch sizes: equal cuts; on the host path the LAST cut is halved again and again down to 8 poses, because the
+     * copy of the last sub-batch is the one thing nothing overlaps (64 poses -> 16 16 16 8 8; 256 -> 64 64 64 32 16 8 8) */
+    std::vector<int> sizes;
+    for (int first = 0; first < n_total; first += poses_per_launch) sizes.push_back(std::min(poses_per_launch, n_total - first));
+    if (copy && sizes.size() >= 2) {
+        int last = sizes.back();
+        sizes.pop_back();
+        while (last >= 16) { sizes.push_back(last - last / 2); last /= 2; }
+        sizes.push_back(last);
+    }
+    const int n_sub = (int)sizes.size();
     const int lanes_used = std::min(n_lanes, n_sub);
     if (copy) {
         while ((int)ctx->sub_ev.size() < n_sub) {
             cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); ctx->sub_ev.push_back(ev);
         }
+        while ((int)ctx->drawn_ev.size() < n_sub) {
+            cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); ctx->drawn_ev.push_back(ev);
+        }
         copy->n_sub = n_sub; copy->ranges.clear();
     }
     CK(cudaEventRecord(ctx->fork_ev, st));
     for (int l = 0; l < lanes_used; l++) CK(cudaStreamWaitEvent(ctx->lanes[l].stream, ctx->fork_ev, 0));
-    int sub = 0;
-    for (int first = 0; first < n_total; first += poses_per_launch, sub++) {
+    for (int sub = 0, first = 0; sub < n_sub; first += sizes[sub], sub++) {
         const int lane = sub % lanes_used;
         cudaStream_t ls = ctx->lanes[lane].stream;
         bind_lane(ctx, P, lane);
-        const int n = std::min(poses_per_launch, n_total - first);
+        const int n = sizes[sub];
         P.n_poses = n;
         P.poses = poses0 + (size_t)first * (P.pose_per_azimuth ? RR_N_ANGLES : 1);
         P.out = out0 + (size_t)first * out_stride;
@@ -838,7 +872,7 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         P.super_stride = P.group_cap / RR_SCAN_BLOCK + 2; P.item_super_stride = items / RR_SCAN_BLOCK + 2;
         {
             uint32_t* t = ctx->lanes[lane].d_tables;
-            P.pass_total = t; P.work_counter = t + (RR_MAX_PASSES + 1); t += 2 * RR_MAX_PASSES + 2;
+            P.pass_total = t; P.work_counter = t + (RR_MAX_PASSES + 1); t += 3 * RR_MAX_PASSES + 3;
             P.item_start = t; t += (size_t)(Pn + 1) * P.item_stride;
             P.super_count = t; t += (size_t)(Pn + 1) * P.super_stride;
             P.item_super = t; t += (size_t)(Pn + 1) * P.item_super_stride;
@@ -854,8 +888,17 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         if (timed) CK(cudaEventRecord(te[0], ls));
         for (int pass = 0; pass < Pn; pass++) {
             /* later lists can be up to 2^pass times longer than list 0: keep the full persistent grid for them */
-            CK(rr_launch_trace(&P, pass, pass == 0 ? grid : ctx->grid, ls, stats, debug));
-            ctx->launches++;
+            if (ctx->split_pass) {
+                /* cast and shading as two kernels, each with its own register budget and persistent grid */
+                const uint32_t gw = (uint32_t)(ctx->num_sms * ctx->walk_ctas_per_sm), gs = (uint32_t)(ctx->num_sms * ctx->shade_ctas_per_sm);
+                const uint32_t need = (groups0 + warps_per_cta - 1) / warps_per_cta;
+                CK(rr_launch_walk(&P, pass, (int)std::max(1u, pass == 0 ? std::min(gw, need) : gw), ls, stats));
+                CK(rr_launch_shade(&P, pass, (int)std::max(1u, pass == 0 ? std::min(gs, need) : gs), ls, debug));
+                ctx->launches += 2;
+            } else {
+                CK(rr_launch_trace(&P, pass, pass == 0 ? grid : ctx->grid, ls, stats, debug));
+                ctx->launches++;
+            }
             if (pass + 1 < Pn) { CK(rr_launch_scan(&P, pass + 1, ls)); ctx->launches++; }
         }
         if (timed) CK(cudaEventRecord(te[1], ls));
@@ -863,14 +906,22 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         ctx->launches++;
         if (timed) { CK(cudaEventRecord(te[2], ls)); ctx->tev_count++; }
         if (copy) {
-            CK(cudaMemcpyAsync(copy->h_dst + (size_t)first * out_stride, P.out, (size_t)n * out_stride, cudaMemcpyDeviceToHost, ls));
-            CK(cudaEventRecord(ctx->sub_ev[sub], ls));
+            /* the image copy runs on its own stream behind the sub-batch's draw kernel: the lane goes straight on to its
+             * next sub-batch (every sub-batch owns its slice of d_out, so nothing is overwritten before it has left) */
+            CK(cudaEventRecord(ctx->drawn_ev[sub], ls));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->drawn_ev[sub], 0));
+            CK(cudaMemcpyAsync(copy->h_dst + (size_t)first * out_stride, P.out, (size_t)n * out_stride, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->sub_ev[sub], ctx->copy_stream));
             copy->ranges.push_back(std::make_pair(first, n));
         }
     }
     for (int l = 0; l < lanes_used; l++) {
         CK(cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].stream));
         CK(cudaStreamWaitEvent(st, ctx->lanes[l].done, 0));
+    }
+    if (copy) {
+        CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
     }
     P.n_poses = n_total; P.poses = poses0; P.out = out0; P.frame_id0 = frame0; P.peer_pose0 = 0;
     P.materials = mat0; P.beam_dirs = beam0; P.pose_passes = passes0; P.mat_pairs = pairs0;
@@ -1326,7 +1377,7 @@ int rr_debug_trace(rr_ctx* ctx, const rr_pose* Tsm, uint64_t frame_id0,
     /* the reference's list order: for azimuth, for pass: that azimuth's run of the pass list */
     std::vector<uint32_t> totals(RR_MAX_PASSES + 1), starts((size_t)(Pn + 1) * istride);
     CKD(cudaMemcpy(totals.data(), ctx->lanes[0].d_tables, totals.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CKD(cudaMemcpy(starts.data(), ctx->lanes[0].d_tables + (2 * RR_MAX_PASSES + 2), starts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CKD(cudaMemcpy(starts.data(), ctx->lanes[0].d_tables + (3 * RR_MAX_PASSES + 3), starts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     size_t nc = 0, ns = 0;
     std::vector<rr_cast_record> hc; std::vector<rr_signal_record> hs;
     if (casts) { hc.resize(Pn * wcap); CKD(cudaMemcpy(hc.data(), d_casts, hc.size() * sizeof(rr_cast_record), cudaMemcpyDeviceToHost)); }

@@ -142,7 +142,8 @@ struct RRFrameParams {
     int2* sig_cell;                /* [n_passes][wave_cap] range cells of the (path, multipath) return of wave j */
     float2* sig_strength;          /* [n_passes][wave_cap] */
     /* control + counters */
-    uint32_t* work_counter;        /* [RR_MAX_PASSES] next group of pass p */
+    uint32_t* work_counter;        /* [2][RR_MAX_PASSES + 1] next group of pass p (second row: rr_shade_kernel when the pass runs as two kernels) */
+    int2* hit_rec;                 /* [wave_cap] (triangle slot or -1, range bits) of wave j: rr_walk_kernel -> rr_shade_kernel */
     unsigned long long* counters;  /* [0] casts [1] hits [2] signals [3] nodes [4] tris [5] max_waves */
     int32_t* error_flags;          /* [0] wave overflow [1] object/material id out of range */
     /* debug (rr_debug_trace) */

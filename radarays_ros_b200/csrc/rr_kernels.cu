@@ -77,11 +77,50 @@ __device__ __forceinline__ float rr_plane(uint32_t w, uint32_t sel, uint32_t mag
     return __uint_as_float(r);
 }
 
+/* Blackwell's packed single-precision FMA (fma.rn.f32x2 -> FFMA2): two independent IEEE fmas per issue slot. The walk
+ * is issue-bound, so pairing the twelve plane distances of a node step (x with y of one child and plane kind, the z
+ * planes of both children) halves their FFMA issue slots. Element results are those of two scalar fmaf. */
+#ifndef RR_FFMA2
+#define RR_FFMA2 0
+#endif
+__device__ __forceinline__ uint64_t rr_pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void rr_ffma2(float& x, float& y, float fx, float fy, uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(rr_pack2(fx, fy)), "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(d));
+}
+
+__device__ __forceinline__ uint32_t rr_pop_local(uint32_t& sp)
+{
+    uint32_t v;
+    sp -= 4;
+    asm volatile("{ .reg .u64 a; cvt.u64.u32 a, %1; ld.local.u32 %0, [a]; }" : "=r"(v) : "r"(sp) : "memory");
+    return v;
+}
+
 /* Traversal stack: the first RR_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread]
  * (a warp's accesses never conflict whatever the lanes' depths are); only deeper entries (rare: the stack holds one
  * postponed sibling per "both children hit" node of the current path) go to the thread's local-memory array. */
 #ifndef RR_SMEM_STACK
 #define RR_SMEM_STACK 0             /* measured on the B200 (urban-5M, 16 poses): 0 -> 1.591 ms, 16 -> 1.697, 24 -> 1.695, 32 -> 1.735: the shared-memory stack costs L1 capacity (the node gathers live there) and a branch per push/pop */
+#endif
+#ifndef RR_STACK_PTR
+#define RR_STACK_PTR 1
+#endif
+/* RR_EARLY_EXIT = T > 0: the warp leaves the node loop as soon as at most T of its lanes are still descending (one vote
+ * per node step) instead of waiting for the last one; the stragglers idle through the leaf tests and walk on afterwards.
+ * Every ray still visits its own nodes in its own order, so hits and counters do not change. 0 = plain while-while. */
+#ifndef RR_LDG256
+#define RR_LDG256 0
+#endif
+#ifndef RR_EARLY_EXIT
+#define RR_EARLY_EXIT 0
 #endif
 #define RR_TRACE_SMEM_BYTES ((size_t)RR_SMEM_STACK * RR_TRACE_BLOCK * sizeof(uint32_t))
 
@@ -89,7 +128,7 @@ template <bool STATS>
 __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const float4* __restrict__ tris,
                                         uint32_t root_ref, const float* go, const float* gs,
                                         rr_vec3 o, rr_vec3 d, float tmax, float& t_hit, int& face_hit,
-                                        unsigned& n_nodes, unsigned& n_tris, uint32_t* s_stack)
+                                        unsigned& n_nodes, unsigned& n_tris, uint32_t* s_stack, unsigned wmask)
 {
     /* plane distance in ray space (rr_internal.h): t = f*A + B', f = 2^23 + q. One PRMT + one FFMA per plane; the
      * near/far plane of each axis is chosen by the per-ray selectors, so no per-axis min/max is needed. */
@@ -103,17 +142,31 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
     const uint32_t nz = (iz >= 0.f) ? 0x7610u : 0x7632u, fz = nz ^ 0x0022u;
     uint32_t magic;
     asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));   /* kept in a register: PRMT's third operand */
+#if RR_FFMA2
+    const uint64_t Axy = rr_pack2(sax, say), Bxy = rr_pack2(sbx, sby), Azz = rr_pack2(saz, saz), Bzz = rr_pack2(sbz, sbz);
+#endif
 #if RR_SMEM_STACK > 0
-    uint32_t stack[RR_STACK_SIZE - RR_SMEM_STACK];
+    uint32_t stack[RR_STACK_SIZE + 1 - RR_SMEM_STACK];
     uint32_t* const sst = s_stack + threadIdx.x;                     /* entry k of this thread: sst[k * blockDim.x] */
 #define RR_PUSH(v) do { if (sp < RR_SMEM_STACK) sst[sp * RR_TRACE_BLOCK] = (v); else stack[sp - RR_SMEM_STACK] = (v); sp++; } while (0)
 #define RR_POP() ((--sp < RR_SMEM_STACK) ? sst[sp * RR_TRACE_BLOCK] : stack[sp - RR_SMEM_STACK])
+    int sp = 0;
+#elif RR_STACK_PTR
+    /* the stack pointer IS the entry's local-memory address: push and pop need no index scaling (one instruction less
+     * each than stack[sp++] / stack[--sp]) */
+    uint32_t stack[RR_STACK_SIZE + 1];
+    uint32_t sp;                                       /* local-window addresses fit 32 bits */
+    { uint64_t a; asm volatile("cvta.to.local.u64 %0, %1;" : "=l"(a) : "l"(stack) : "memory"); sp = (uint32_t)a; }
+#define RR_PUSH(v) do { asm volatile("{ .reg .u64 a; cvt.u64.u32 a, %0; st.local.u32 [a], %1; }" :: "r"(sp), "r"(v) : "memory"); sp += 4; } while (0)
+#define RR_POP() rr_pop_local(sp)
 #else
-    uint32_t stack[RR_STACK_SIZE];
+    uint32_t stack[RR_STACK_SIZE + 1];
 #define RR_PUSH(v) do { stack[sp++] = (v); } while (0)
 #define RR_POP() (stack[--sp])
-#endif
     int sp = 0;
+#endif
+    /* sentinel at the bottom: popping it ends the walk, so no pop ever tests for an empty stack */
+    RR_PUSH(RR_REF_EMPTY);
     uint32_t cur = root_ref;
     float best_t = INFINITY;
     int best_face = -1, best_slot = -1;
@@ -123,56 +176,91 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
      * lanes of the warp reconverge after the inner loop, so the triangle tests below run once per round with (nearly)
      * all lanes on a leaf instead of being replayed for one or two lanes between node steps. RR_REF_EMPTY (which has
      * the leaf bit set, so it also ends the inner loop) marks a finished lane. */
-    while (cur != RR_REF_EMPTY) {
-        while (!(cur & RR_REF_LEAF)) {
-            const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
-            const uint4 a = __ldg(np);           /* c0.x c0.y c0.z c1.x */
-            const uint4 b = __ldg(np + 1);       /* c1.y c1.z ref0 ref1 */
-            if (STATS) n_nodes++;
-            const float t0n = fmaxf(fmaxf(fmaf(rr_plane(a.x, nx, magic), sax, sbx), fmaf(rr_plane(a.y, ny, magic), say, sby)),
-                                    fmaxf(fmaf(rr_plane(a.z, nz, magic), saz, sbz), 0.0f));
-            const float t0f = fminf(fminf(fmaf(rr_plane(a.x, fx, magic), sax, sbx), fmaf(rr_plane(a.y, fy, magic), say, sby)),
-                                    fminf(fmaf(rr_plane(a.z, fz, magic), saz, sbz), limit));
-            const float t1n = fmaxf(fmaxf(fmaf(rr_plane(a.w, nx, magic), sax, sbx), fmaf(rr_plane(b.x, ny, magic), say, sby)),
-                                    fmaxf(fmaf(rr_plane(b.y, nz, magic), saz, sbz), 0.0f));
-            const float t1f = fminf(fminf(fmaf(rr_plane(a.w, fx, magic), sax, sbx), fmaf(rr_plane(b.x, fy, magic), say, sby)),
-                                    fminf(fmaf(rr_plane(b.y, fz, magic), saz, sbz), limit));
-            const bool h0 = (t0n <= t0f);        /* an absent child (meshes with < 2 leaves) carries an inverted box */
-            const bool h1 = (t1n <= t1f);        /* (rr_bvh_pack), which no ray enters: its ref is never followed */
-            /* (a select-only form of the four outcomes below — no divergent paths inside the step — measured slower:
-             * 1.636 vs 1.594 ms per 16-pose step; the short divergent arms cost less than the extra selects) */
-            if (h0 && h1) {
-                const bool first0 = t0n <= t1n;
-                cur = first0 ? b.z : b.w;
-                if (sp < RR_STACK_SIZE) RR_PUSH(first0 ? b.w : b.z);
-            } else if (h0) {
-                cur = b.z;
-            } else if (h1) {
-                cur = b.w;
-            } else {
-                cur = (sp > 0) ? RR_POP() : RR_REF_EMPTY;
-            }
+    /* one node step of this lane's ray: both child boxes, next = nearer hit child, the other one postponed */
+    auto node_step = [&]() {
+#if RR_LDG256
+        uint4 a, b;                          /* the whole 32-byte node in one 256-bit load (sm_100: LDG.E.ENL2.256) */
+        asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(nodes + cur));
+#else
+        const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
+        const uint4 a = __ldg(np);           /* c0.x c0.y c0.z c1.x */
+        const uint4 b = __ldg(np + 1);       /* c1.y c1.z ref0 ref1 */
+#endif
+        if (STATS) n_nodes++;
+#if RR_FFMA2
+        float c0nx, c0ny, c0fx, c0fy, c1nx, c1ny, c1fx, c1fy, c0nz, c1nz, c0fz, c1fz;
+        rr_ffma2(c0nx, c0ny, rr_plane(a.x, nx, magic), rr_plane(a.y, ny, magic), Axy, Bxy);
+        rr_ffma2(c0fx, c0fy, rr_plane(a.x, fx, magic), rr_plane(a.y, fy, magic), Axy, Bxy);
+        rr_ffma2(c1nx, c1ny, rr_plane(a.w, nx, magic), rr_plane(b.x, ny, magic), Axy, Bxy);
+        rr_ffma2(c1fx, c1fy, rr_plane(a.w, fx, magic), rr_plane(b.x, fy, magic), Axy, Bxy);
+        rr_ffma2(c0nz, c1nz, rr_plane(a.z, nz, magic), rr_plane(b.y, nz, magic), Azz, Bzz);
+        rr_ffma2(c0fz, c1fz, rr_plane(a.z, fz, magic), rr_plane(b.y, fz, magic), Azz, Bzz);
+        const float t0n = fmaxf(fmaxf(c0nx, c0ny), fmaxf(c0nz, 0.0f));
+        const float t0f = fminf(fminf(c0fx, c0fy), fminf(c0fz, limit));
+        const float t1n = fmaxf(fmaxf(c1nx, c1ny), fmaxf(c1nz, 0.0f));
+        const float t1f = fminf(fminf(c1fx, c1fy), fminf(c1fz, limit));
+#else
+        const float t0n = fmaxf(fmaxf(fmaf(rr_plane(a.x, nx, magic), sax, sbx), fmaf(rr_plane(a.y, ny, magic), say, sby)),
+                                fmaxf(fmaf(rr_plane(a.z, nz, magic), saz, sbz), 0.0f));
+        const float t0f = fminf(fminf(fmaf(rr_plane(a.x, fx, magic), sax, sbx), fmaf(rr_plane(a.y, fy, magic), say, sby)),
+                                fminf(fmaf(rr_plane(a.z, fz, magic), saz, sbz), limit));
+        const float t1n = fmaxf(fmaxf(fmaf(rr_plane(a.w, nx, magic), sax, sbx), fmaf(rr_plane(b.x, ny, magic), say, sby)),
+                                fmaxf(fmaf(rr_plane(b.y, nz, magic), saz, sbz), 0.0f));
+        const float t1f = fminf(fminf(fmaf(rr_plane(a.w, fx, magic), sax, sbx), fmaf(rr_plane(b.x, fy, magic), say, sby)),
+                                fminf(fmaf(rr_plane(b.y, fz, magic), saz, sbz), limit));
+#endif
+        const bool h0 = (t0n <= t0f);        /* an absent child (meshes with < 2 leaves) carries an inverted box */
+        const bool h1 = (t1n <= t1f);        /* (rr_bvh_pack), which no ray enters: its ref is never followed */
+        /* (a select-only form of the four outcomes below — no divergent paths inside the step — measured slower:
+         * 1.636 vs 1.594 ms per 16-pose step; the short divergent arms cost less than the extra selects) */
+        if (h0 && h1) {
+            const bool first0 = t0n <= t1n;
+            cur = first0 ? b.z : b.w;
+            RR_PUSH(first0 ? b.w : b.z);   /* cannot overflow: the stack holds at most one postponed sibling per level of the
+                                              current path and rr_set_mesh rejects a BVH deeper than RR_STACK_SIZE */
+        } else if (h0) {
+            cur = b.z;
+        } else if (h1) {
+            cur = b.w;
+        } else {
+            cur = RR_POP();
         }
-        if (cur != RR_REF_EMPTY) {
-            const uint32_t first = cur & 0x0fffffffu;
-            const uint32_t cnt = ((cur >> 28) & 7u) + 1u;
-            for (uint32_t k = 0; k < cnt; k++) {
-                const float4 q0 = __ldg(tris + 3 * (first + k));
-                const float4 q1 = __ldg(tris + 3 * (first + k) + 1);
-                const float4 q2 = __ldg(tris + 3 * (first + k) + 2);
-                if (STATS) n_tris++;
-                float t;
-                if (rr_ray_triangle(o, d, rr_v3(q0.x, q0.y, q0.z), rr_v3(q1.x, q1.y, q1.z), rr_v3(q2.x, q2.y, q2.z), tmax, &t)) {
-                    const int face = (int)__float_as_uint(q0.w);
-                    if (best_face < 0 || t < best_t || (t == best_t && face < best_face)) {
-                        best_t = t; best_face = face; best_slot = (int)(first + k);
-                        limit = best_t * 1.00001f + 1e-6f;
-                    }
+    };
+    /* the triangles of the leaf `cur` holds, then the next postponed subtree */
+    auto leaf_step = [&]() {
+        const uint32_t first = cur & 0x0fffffffu;
+        const uint32_t cnt = ((cur >> 28) & 7u) + 1u;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const float4 q0 = __ldg(tris + 3 * (first + k));
+            const float4 q1 = __ldg(tris + 3 * (first + k) + 1);
+            const float4 q2 = __ldg(tris + 3 * (first + k) + 2);
+            if (STATS) n_tris++;
+            float t;
+            if (rr_ray_triangle(o, d, rr_v3(q0.x, q0.y, q0.z), rr_v3(q1.x, q1.y, q1.z), rr_v3(q2.x, q2.y, q2.z), tmax, &t)) {
+                const int face = (int)__float_as_uint(q0.w);
+                if (best_face < 0 || t < best_t || (t == best_t && face < best_face)) {
+                    best_t = t; best_face = face; best_slot = (int)(first + k);
+                    limit = best_t * 1.00001f + 1e-6f;
                 }
             }
-            cur = (sp > 0) ? RR_POP() : RR_REF_EMPTY;
         }
+        cur = RR_POP();
+    };
+#if RR_EARLY_EXIT > 0
+    for (;;) {
+        do {
+            if (!(cur & RR_REF_LEAF)) node_step();
+        } while (__popc(__ballot_sync(wmask, !(cur & RR_REF_LEAF))) > RR_EARLY_EXIT);
+        if ((cur & RR_REF_LEAF) && cur != RR_REF_EMPTY) leaf_step();
+        if (!__any_sync(wmask, cur != RR_REF_EMPTY)) break;
     }
+#else
+    while (cur != RR_REF_EMPTY) {
+        while (!(cur & RR_REF_LEAF)) node_step();
+        if (cur != RR_REF_EMPTY) leaf_step();
+    }
+#endif
 #undef RR_PUSH
 #undef RR_POP
     t_hit = best_t;
@@ -305,10 +393,14 @@ __global__ void __launch_bounds__(128) rr_mat_pairs_kernel(const float4* __restr
  * pass 0). A group appends its surviving children in the reference's order (RadarCPU.cpp:243,290,369: parents in list
  * order, reflection before refraction) by ballot/popc compaction into its own 64 slots; no barrier, no shared memory.
  * ---------------------------------------------------------------------------------------------- */
-template <bool STATS, bool DEBUG>
-__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel(const RRFrameParams P, const int pass)
+/* MODE 0: the whole pass in one kernel (rr_trace_kernel). MODE 1 / 2: the pass as two kernels — rr_walk_kernel only casts
+ * (closest hit -> hit_rec[j] = (triangle slot, range)) with the small register budget of the walk, rr_shade_kernel reads
+ * the hit records and does everything after the cast with the registers the fp64 shading wants. Same code, same order,
+ * same bits; which form runs is a host-side switch (rr_api.cu). */
+enum { RR_PASS_FUSED = 0, RR_PASS_WALK = 1, RR_PASS_SHADE = 2 };
+template <bool STATS, bool DEBUG, int MODE>
+__device__ __forceinline__ void rr_pass_body(const RRFrameParams& P, const int pass, uint32_t* s_trace_stack)
 {
-    extern __shared__ uint32_t s_trace_stack[];
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t S = (uint32_t)P.n_samples;
@@ -339,11 +431,12 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
 
     while (true) {
         uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(P.work_counter + pass, 1u);
+        if (lane == 0) g = atomicAdd(P.work_counter + (MODE == RR_PASS_SHADE ? RR_MAX_PASSES + 1 : 0) + pass, 1u);
         g = __shfl_sync(RR_FULL, g, 0);
         if (g >= n_groups) break;
         const uint32_t j = g * 32u + (uint32_t)lane;
         const bool active = j < n_in;
+        const uint32_t act_mask = __ballot_sync(RR_FULL, active);
 
         uint32_t item = 0;
         bool keep0 = false, keep1 = false, hit = false;
@@ -387,9 +480,17 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
             if (pass == 0) { const float4 x0 = __ldg(P.item_xf + 3 * (size_t)item + 2); o_m = rr_v3(x0.x, x0.y, x0.z); }
             else o_m = rr_add(RR_QROT(R, w.o), rr_v3(xt.x, xt.y, xt.z));
             const rr_vec3 d_m = RR_QROT(R, w.d);
-            const int slot_t = rr_trace<STATS>(P.nodes, P.tris, P.root_ref, go, gs, o_m, d_m, 1000.0f,
-                                               range, face, stat_nodes, stat_tris, s_trace_stack);
-            if (slot_t >= 0) {
+            int slot_t;
+            if (MODE == RR_PASS_SHADE) {
+                const int2 hr = __ldcs(P.hit_rec + j);
+                slot_t = hr.x; range = __int_as_float(hr.y);
+                if (DEBUG && slot_t >= 0) face = (int)__float_as_uint(__ldg(P.tris + 3 * slot_t).w);
+            } else {
+                slot_t = rr_trace<STATS>(P.nodes, P.tris, P.root_ref, go, gs, o_m, d_m, 1000.0f,
+                                         range, face, stat_nodes, stat_tris, s_trace_stack, act_mask);
+            }
+            if (MODE == RR_PASS_WALK) __stcs(P.hit_rec + j, make_int2(slot_t, __float_as_int(range)));
+            if (MODE != RR_PASS_WALK && slot_t >= 0) {
                 const float4 q1 = __ldg(P.tris + 3 * slot_t + 1);
                 const float4 q2 = __ldg(P.tris + 3 * slot_t + 2);
                 const uint32_t obj = __float_as_uint(q1.w);
@@ -490,9 +591,11 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
             }
             /* returns of wave j, in the order RadarCPU.cpp:322,358 appends them; a slot without a return (and a return
              * whose time is not a number, which can not reach a bin either) carries cell INT32_MIN */
-            __stcs(sg_cell + j, make_int2((n_sig >= 1) ? sig_cell0 : INT32_MIN, (n_sig >= 2) ? sig_cell1 : INT32_MIN));
-            if (n_sig) __stcs(sg_str + j, make_float2(sig_s0, sig_s1));
-            if (DEBUG) {
+            if (MODE != RR_PASS_WALK) {
+                __stcs(sg_cell + j, make_int2((n_sig >= 1) ? sig_cell0 : INT32_MIN, (n_sig >= 2) ? sig_cell1 : INT32_MIN));
+                if (n_sig) __stcs(sg_str + j, make_float2(sig_s0, sig_s1));
+            }
+            if (DEBUG && MODE != RR_PASS_WALK) {
                 const size_t r0 = (size_t)pass * P.wave_cap + j;
                 rr_cast_record r; r.azimuth = az; r.pass = pass; r.face_id = hit ? face : -1;
                 r.range = hit ? range : 0.f; r.energy = dbg_energy; r.n_children = (int)n_child;
@@ -503,10 +606,10 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
             }
         }
 
+        if (MODE == RR_PASS_WALK) continue;            /* the walk kernel only casts */
         /* ordered compaction inside the group (reflection before refraction, parents in list order).
          * The reference also builds waves_new in its last pass and drops it (RadarCPU.cpp:380-389):
          * nothing traces those waves, so the last pass appends none (n_children is still reported). */
-        const uint32_t act_mask = __ballot_sync(RR_FULL, active);
         warp_casts += __popc(act_mask);
         warp_hits += __popc(__ballot_sync(RR_FULL, hit));
         warp_sigs += __popc(__ballot_sync(RR_FULL, n_sig >= 1)) + __popc(__ballot_sync(RR_FULL, n_sig >= 2));
@@ -558,6 +661,30 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel
             atomicAdd(&P.counters[4], (unsigned long long)stat_tris);
         }
     }
+}
+
+template <bool STATS, bool DEBUG>
+__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_MIN_BLOCKS) rr_trace_kernel(const RRFrameParams P, const int pass)
+{
+    extern __shared__ uint32_t s_trace_stack[];
+    rr_pass_body<STATS, DEBUG, RR_PASS_FUSED>(P, pass, s_trace_stack);
+}
+#ifndef RR_WALK_MIN_BLOCKS
+#define RR_WALK_MIN_BLOCKS 12      /* resident 128-thread CTAs per SM of the cast-only kernel (40 registers) */
+#endif
+#ifndef RR_SHADE_MIN_BLOCKS
+#define RR_SHADE_MIN_BLOCKS 8      /* ... of the shading kernel (64 registers) */
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_WALK_MIN_BLOCKS) rr_walk_kernel(const RRFrameParams P, const int pass)
+{
+    extern __shared__ uint32_t s_trace_stack[];
+    rr_pass_body<STATS, false, RR_PASS_WALK>(P, pass, s_trace_stack);
+}
+template <bool DEBUG>
+__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_SHADE_MIN_BLOCKS) rr_shade_kernel(const RRFrameParams P, const int pass)
+{
+    rr_pass_body<false, DEBUG, RR_PASS_SHADE>(P, pass, nullptr);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1144,7 +1271,7 @@ __global__ void rr_cast_kernel(const RRNode* nodes, const float4* tris, uint32_t
     unsigned a = 0, b = 0;
     float t; int face;
     rr_trace<false>(nodes, tris, root_ref, go, gs, rr_v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
-                    rr_v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmax, t, face, a, b, s_cast_stack);
+                    rr_v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tmax, t, face, a, b, s_cast_stack, __activemask());
     face_ids[i] = face;
     ranges[i] = t;
 }
@@ -1223,6 +1350,28 @@ extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, cudaS
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm)
 {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rr_trace_kernel<false, false>, RR_TRACE_BLOCK, RR_TRACE_SMEM_BYTES);
+}
+
+/* the pass as two kernels (rr_pass_body): resident CTAs per SM of each */
+extern "C" cudaError_t rr_split_occupancy(int* walk_blocks_per_sm, int* shade_blocks_per_sm)
+{
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(walk_blocks_per_sm, rr_walk_kernel<false>, RR_TRACE_BLOCK, RR_TRACE_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, rr_shade_kernel<false>, RR_TRACE_BLOCK, 0);
+}
+
+extern "C" cudaError_t rr_launch_walk(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats)
+{
+    if (stats) rr_walk_kernel<true><<<grid, RR_TRACE_BLOCK, RR_TRACE_SMEM_BYTES, st>>>(*P, pass);
+    else rr_walk_kernel<false><<<grid, RR_TRACE_BLOCK, RR_TRACE_SMEM_BYTES, st>>>(*P, pass);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t rr_launch_shade(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int debug)
+{
+    if (debug) rr_shade_kernel<true><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    else rr_shade_kernel<false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    return cudaGetLastError();
 }
 
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
