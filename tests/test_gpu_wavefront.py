@@ -174,3 +174,26 @@ def test_pass_as_two_kernels_matches_the_fused_kernel(oracle_mod, monkeypatch):
     assert out["1"][3] > out["0"][3], "the split form launches one more kernel per pass"
     o = oracle_mod.OracleScene(sc).simulate(cfg, radar.getBeamSamples(), poses[1:2], noise_seed=4, frame_id=10)
     assert np.array_equal(out["1"][1], o["image"])
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_call_sub_batches_and_copy_stream(pinned):
+    """A 70-pose host call is cut into sub-batches 18 18 18 8 8 (rr_api.cu: equal cuts, the last one halved down to 8 so
+    that the only exposed image copy is small) whose images leave on the copy stream while the next sub-batch computes.
+    Every frame must equal the same pose rendered alone with the same frame id, for a page-locked and a pageable buffer."""
+    import torch
+    sc = scenes.box_room_cylinder()
+    cfg = RadarModelConfig(n_reflections=2, n_samples=8, n_cells=256, ambient_noise=2, include_motion=0)
+    radar = RadarB200(sc, cfg, beam_seed=11, noise_seed=12)
+    base = sc.pose_array()[0]
+    poses = (Pose * 70)()
+    for i in range(70):
+        poses[i] = Pose.from_xyz_yaw(base.tx + 0.05 * i, base.ty - 0.03 * i, base.tz, 0.01 * i)
+    out = torch.empty((70, 256, 400), dtype=torch.uint8, pin_memory=True).numpy() if pinned else np.empty((70, 256, 400), np.uint8)
+    out[:] = 7
+    imgs = radar.simulate(poses, frame_id=1000, out=out)
+    assert imgs.shape == (70, 256, 400)
+    for i in (0, 17, 18, 35, 36, 53, 54, 61, 62, 69):
+        single = radar.simulate(poses[i], frame_id=1000 + i)
+        assert np.array_equal(single, imgs[i]), "frame %d of the 70-pose call differs from the pose rendered alone" % i
+    assert len({imgs[i].tobytes() for i in (0, 18, 54, 62, 69)}) == 5
