@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug: small meshes instead of urban-5M / warehouse-1M")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames in the bounded cpu_baseline sample (~10 s of host work)")
     ap.add_argument("--e2e-call", type=int, default=4, help="e2e leg: steps per host call (4 = 64 poses per rr_simulate call)")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic only: skip the L2 flush between timed steps (the line says so)")
     ap.add_argument("--lanes", type=int, default=2, help="internal streams per call (rr_set_lanes); 1 = serial launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -391,7 +392,8 @@ def main():
     wall0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for s in range(K):
-            flush.fill_(s & 0xff)                       # L2 flush between timed iterations (outside the event pair)
+            if not args.no_flush:
+                flush.fill_(s & 0xff)                   # L2 flush between timed iterations (outside the event pair)
             evs[s][0].record(stream)
             step((W + s) * PPS)
             evs[s][1].record(stream)
@@ -419,7 +421,8 @@ def main():
     KR = max(1, min(K, 200 // seq_per_step))               # the library remembers 256 launch pairs
     with torch.cuda.stream(stream):
         for s in range(KR):
-            flush.fill_(s & 0xff)
+            if not args.no_flush:
+                flush.fill_(s & 0xff)
             step((W + s) * PPS)
     torch.cuda.synchronize()
     trace_ms_sum, draw_ms_sum, n_pairs = radar.kernel_times()     # events around the kernels, on the launch stream
@@ -605,7 +608,8 @@ def main():
             "dtype": "f32 geometry / f64 wave scalars", "data": "synthetic",
             "config": {"workload": wl.describe(scene), "baseline_config": args.config, "n_triangles": scene.n_tris,
                        "poses_per_step": PPS, "shard": shard,
-                       "l2": "flushed between timed steps (256 MiB write outside the event pair); mesh+BVH %.0f MB > L2" % (st.bvh_bytes / 1e6),
+                       "l2": ("flushed between timed steps (256 MiB write outside the event pair); mesh+BVH %.0f MB > L2" % (st.bvh_bytes / 1e6))
+                             if not args.no_flush else "NOT flushed (--no-flush: diagnostic run, not a bench value)",
                        "parallelism": par, "bvh_build_ms": st.bvh_build_ms, "scene_gen_s": t_scene},
             "rays_bounces_per_s": casts_all * K / (total_ms_max / 1000.0),
             "casts_per_step": casts_all, "image_checksum": img_sum,
