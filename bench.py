@@ -375,7 +375,8 @@ def main():
     radar.setStatsMode(False)
     cols_mine = azimuth_shard(rank, world)[1] if sharded is not None else N_ANGLES
     img_bytes_step = n_mine * cols_mine * N_CELLS
-    alg_bytes = 32 * nodes + 48 * tris + 4 * hits + img_bytes_step
+    node_bytes = int(round((st.bvh_bytes - 48 * scene.n_tris) / max(st.bvh_nodes, 1)))      # 32 (binary node), 64 (RR_WIDE_BVH build)
+    alg_bytes = node_bytes * nodes + 48 * tris + 4 * hits + img_bytes_step
 
     with torch.cuda.stream(stream):
         for w in range(W):
@@ -560,7 +561,7 @@ def main():
     if rank == 0:
         peak, peak_src = peak_hbm()
         # dominant kernel = rr_trace_kernel: its algorithmic gather bytes over ITS average duration per launch sequence
-        trace_bytes = (32 * nodes + 48 * tris + 4 * hits) / seq_per_step
+        trace_bytes = (node_bytes * nodes + 48 * tris + 4 * hits) / seq_per_step
         n_seq = max(n_pairs, 1)
         avg_launch_s = (trace_ms_sum / n_seq) / 1000.0
         achieved = trace_bytes / avg_launch_s / 1e9
@@ -586,7 +587,8 @@ def main():
                 "kernel": "rr_trace_kernel", "kernel_ms": trace_ms_sum / n_seq,
                 "kernel_share_of_step": trace_ms_sum / max(trace_ms_sum + draw_ms_sum, 1e-9),
                 "algorithmic_bytes_per_launch": trace_bytes,
-                "formula": "32 B x nodes_visited + 48 B x tris_tested + 4 B x hits per launch sequence = the %d per-pass launches of rr_trace_kernel over rank 0's poses (32-byte binary BVH node, 48-byte triangle; counted by the counting instantiation of the same kernel; kernel_ms = their summed duration incl. the %d rr_scan_kernel launches between them, CUDA events on the launch stream, one lane)" % (cfg.n_reflections, cfg.n_reflections - 1),
+                "node_bytes": node_bytes,
+                "formula": "node_bytes x nodes_visited + 48 B x tris_tested + 4 B x hits per launch sequence = the %d per-pass launches of rr_trace_kernel over rank 0's poses (32-byte binary BVH node, 48-byte triangle; counted by the counting instantiation of the same kernel; kernel_ms = their summed duration incl. the %d rr_scan_kernel launches between them, CUDA events on the launch stream, one lane)" % (cfg.n_reflections, cfg.n_reflections - 1),
                 "draw_kernel_ms": draw_ms_sum / n_seq, "step_algorithmic_bytes": alg_bytes,
                 "step_achieved_gbs": alg_bytes / ((total_ms / K) / 1000.0) / 1e9,
                 "nodes_visited": nodes, "tris_tested": tris, "nodes_per_cast": nodes / max(casts, 1), "tris_per_cast": tris / max(casts, 1)}

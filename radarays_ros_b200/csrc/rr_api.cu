@@ -28,6 +28,8 @@ extern "C" cudaError_t rr_launch_mat_pairs(const float4* materials, int n_mat, i
 extern "C" cudaError_t rr_launch_draw(const RRFrameParams* P, int n_items, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_trace_occupancy(int* blocks_per_sm);
 extern "C" cudaError_t rr_split_occupancy(int* walk_blocks_per_sm, int* shade_blocks_per_sm);
+extern "C" cudaError_t rr_dual_occupancy(int* blocks_per_sm);
+extern "C" cudaError_t rr_launch_dual(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats, int debug);
 extern "C" cudaError_t rr_launch_walk(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats);
 extern "C" cudaError_t rr_launch_shade(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int debug);
 extern "C" cudaError_t rr_launch_cast(const RRNode* nodes, const float4* tris, uint32_t root_ref, const float* go,
@@ -48,6 +50,7 @@ struct rr_ctx {
     int trace_ctas_per_sm = 0;
     int walk_ctas_per_sm = 0, shade_ctas_per_sm = 0;
     int split_pass = 0;                            /* 1: every pass runs as rr_walk_kernel + rr_shade_kernel instead of rr_trace_kernel */
+    int dual_pass = 0, dual_ctas_per_sm = 0;       /* 1: every pass runs as rr_dual_kernel (two rays per lane) */
     /* scene */
     bool have_mesh = false;
     RRNode* d_nodes = nullptr; float4* d_tris = nullptr;
@@ -453,7 +456,9 @@ int rr_set_mesh(rr_ctx* ctx, const float* verts, size_t n_verts, const uint32_t*
         return fail(ctx, rc, "rr_set_mesh: BVH build failed: %s", berr.c_str());
     }
     /* the walk postpones at most one subtree per inner node of the current path: a deeper tree would overflow its stack */
-    if (bvh.max_depth > RR_STACK_SIZE) {
+    /* worst-case traversal stack: one postponed sibling per level of the path (binary), up to three per folded level (wide) */
+    const int stack_need = RR_WIDE_BVH ? 3 * ((bvh.max_depth + 1) / 2) : bvh.max_depth;
+    if (stack_need > RR_STACK_SIZE) {
         cudaFree(bvh.d_nodes); cudaFree(bvh.d_tris);
         return fail(ctx, RR_ERR_INVALID_ARGUMENT, "rr_set_mesh: BVH depth %d exceeds the traversal stack (%d entries)", bvh.max_depth, RR_STACK_SIZE);
     }
@@ -727,6 +732,9 @@ static int ensure_scratch(rr_ctx* ctx, size_t want_items)
         CK(rr_split_occupancy(&ctx->walk_ctas_per_sm, &ctx->shade_ctas_per_sm));
         if (getenv("RR_PASS_SPLIT")) ctx->split_pass = atoi(getenv("RR_PASS_SPLIT")) ? 1 : 0;
         if (ctx->walk_ctas_per_sm < 1 || ctx->shade_ctas_per_sm < 1) ctx->split_pass = 0;
+        CK(rr_dual_occupancy(&ctx->dual_ctas_per_sm));
+        if (getenv("RR_PASS_DUAL")) ctx->dual_pass = atoi(getenv("RR_PASS_DUAL")) ? 1 : 0;
+        if (ctx->dual_ctas_per_sm < 1) ctx->dual_pass = 0;
     }
     const int per_sm = ctx->trace_ctas_per_sm;
     if (per_sm < 1) return fail(ctx, RR_ERR_CUDA, "trace kernel does not fit on an SM");
@@ -888,7 +896,12 @@ static int enqueue(rr_ctx* ctx, RRFrameParams& P, cudaStream_t st, int stats, in
         if (timed) CK(cudaEventRecord(te[0], ls));
         for (int pass = 0; pass < Pn; pass++) {
             /* later lists can be up to 2^pass times longer than list 0: keep the full persistent grid for them */
-            if (ctx->split_pass) {
+            if (ctx->dual_pass) {
+                const uint32_t gd = (uint32_t)(ctx->num_sms * ctx->dual_ctas_per_sm);
+                const uint32_t need = (groups0 / 2u + warps_per_cta) / warps_per_cta;
+                CK(rr_launch_dual(&P, pass, (int)std::max(1u, pass == 0 ? std::min(gd, need) : gd), ls, stats, debug));
+                ctx->launches++;
+            } else if (ctx->split_pass) {
                 /* cast and shading as two kernels, each with its own register budget and persistent grid */
                 const uint32_t gw = (uint32_t)(ctx->num_sms * ctx->walk_ctas_per_sm), gs = (uint32_t)(ctx->num_sms * ctx->shade_ctas_per_sm);
                 const uint32_t need = (groups0 + warps_per_cta - 1) / warps_per_cta;
@@ -952,7 +965,7 @@ static int collect_finish(rr_ctx* ctx, rr_stats* stats, float kernel_ms)
     rr_stats& s = ctx->last;
     s.n_casts = cnt[0]; s.n_hits = cnt[1]; s.n_signals = cnt[2]; s.nodes_visited = cnt[3]; s.tris_tested = cnt[4];
     s.max_waves = cnt[5]; s.bvh_nodes = ctx->n_nodes;
-    s.bvh_bytes = ctx->n_nodes * sizeof(RRNode) + ctx->n_tris * 3 * sizeof(float4);
+    s.bvh_bytes = ctx->n_nodes * (size_t)RR_NODE_BYTES + ctx->n_tris * 3 * sizeof(float4);
     s.kernel_ms = kernel_ms; s.bvh_build_ms = ctx->bvh_build_ms; s.overflow = flags[0];
     if (stats) *stats = s;
     if (flags[1]) return fail(ctx, RR_ERR_OUT_OF_RANGE, "a hit face carries an object id >= n_objects");

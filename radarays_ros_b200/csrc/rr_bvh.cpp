@@ -198,3 +198,43 @@ void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& bn, cons
         out.nodes[packed_idx[i]] = nd;
     }
 }
+
+/* Fold every second level of the packed binary tree into its parent (the host twin of k_widen, for the tiny meshes the
+ * host builds): kept nodes are those on even levels; their order among themselves stays depth-first. */
+void rr_bvh_widen_host(const std::vector<RRNode>& bin, std::vector<RRNode4>& out)
+{
+    out.clear();
+    if (bin.empty()) return;
+    std::vector<int> level(bin.size(), -1);
+    std::vector<uint32_t> todo(1, 0u);
+    level[0] = 0;
+    while (!todo.empty()) {
+        const uint32_t i = todo.back(); todo.pop_back();
+        const uint32_t ch[2] = {bin[i].c0, bin[i].c1};
+        for (int k = 0; k < 2; k++) if (!(ch[k] & RR_REF_LEAF)) { level[ch[k]] = level[i] + 1; todo.push_back(ch[k]); }
+    }
+    std::vector<uint32_t> widx(bin.size(), 0u);
+    uint32_t n_wide = 0;
+    for (size_t i = 0; i < bin.size(); i++) if (level[i] >= 0 && (level[i] & 1) == 0) widx[i] = n_wide++;
+    out.resize(n_wide);
+    for (size_t i = 0; i < bin.size(); i++) {
+        if (level[i] < 0 || (level[i] & 1)) continue;
+        RRNode4 o;
+        for (int k = 0; k < 12; k++) o.w[k] = 65535u;
+        for (int k = 0; k < 4; k++) o.c[k] = RR_REF_EMPTY;
+        for (int side = 0; side < 2; side++) {
+            const uint32_t ref = side ? bin[i].c1 : bin[i].c0;
+            const uint32_t* wb = bin[i].w + 3 * side;
+            if (ref & RR_REF_LEAF) {
+                for (int a = 0; a < 3; a++) o.w[6 * side + a] = wb[a];
+                o.c[2 * side] = ref;
+            } else {
+                const RRNode& c = bin[ref];
+                for (int k = 0; k < 6; k++) o.w[6 * side + k] = c.w[k];
+                o.c[2 * side] = (c.c0 & RR_REF_LEAF) ? c.c0 : widx[c.c0];
+                o.c[2 * side + 1] = (c.c1 & RR_REF_LEAF) ? c.c1 : widx[c.c1];
+            }
+        }
+        out[widx[i]] = o;
+    }
+}

@@ -37,4 +37,7 @@ void rr_bvh_build_host(const RRTriSoup& soup, std::vector<RRBuildNode>& nodes, s
 /* Quantise + reorder: RRBuildNode tree -> 32-byte nodes + leaf-ordered triangles. */
 void rr_bvh_pack(const RRTriSoup& soup, const std::vector<RRBuildNode>& nodes, const std::vector<uint32_t>& order,
                  RRPackedBVH& out);
+
+/* packed binary nodes (depth-first order, root = node 0) -> 4-wide nodes (RR_WIDE_BVH; rr_internal.h) */
+void rr_bvh_widen_host(const std::vector<RRNode>& bin, std::vector<RRNode4>& out);
 #endif

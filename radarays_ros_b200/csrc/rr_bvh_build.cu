@@ -472,7 +472,7 @@ __global__ void k_subtree_counts(const RRBuildNode* __restrict__ nodes, int n_no
 
 /* depth-first index of every inner node = sum over its path of (1 + inner nodes of the left sibling when coming from the right) */
 __global__ void k_dfs_index(const RRBuildNode* __restrict__ nodes, int n_nodes, const int32_t* __restrict__ parent,
-                            const uint32_t* __restrict__ cnt, uint32_t* packed_idx, int* max_depth)
+                            const uint32_t* __restrict__ cnt, uint32_t* packed_idx, int* max_depth, uint32_t* kept)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int depth = 0;
@@ -486,6 +486,7 @@ __global__ void k_dfs_index(const RRBuildNode* __restrict__ nodes, int n_nodes, 
             node = p; depth++;
         }
         packed_idx[i] = idx;
+        if (kept) kept[idx] = (uint32_t)(depth & 1);       /* wide build: nodes on even levels (root = level 0, depth 1) survive */
     }
     for (int off = 16; off > 0; off >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, off));
     if ((threadIdx.x & 31) == 0 && depth) atomicMax(max_depth, depth);
@@ -521,6 +522,33 @@ __global__ void k_pack_nodes(const RRBuildNode* __restrict__ nodes, int n_nodes,
     o.c0 = (L.left >= 0) ? packed_idx[nd.left] : (RR_REF_LEAF | ((uint32_t)(L.count - 1) << 28) | (uint32_t)L.first);
     o.c1 = (R.left >= 0) ? packed_idx[nd.right] : (RR_REF_LEAF | ((uint32_t)(R.count - 1) << 28) | (uint32_t)R.first);
     out[packed_idx[i]] = o;
+}
+
+/* binary packed nodes (depth-first order) -> 4-wide nodes: every kept node takes the children of its inner children.
+ * widx[] = exclusive prefix of kept[] = depth-first index among the kept nodes (folding preserves the preorder). */
+__global__ void k_widen(const RRNode* __restrict__ bin, int n_bin, const uint32_t* __restrict__ kept,
+                        const uint32_t* __restrict__ widx, RRNode4* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bin || !kept[i]) return;
+    const RRNode nd = bin[i];
+    RRNode4 o;
+    for (int k = 0; k < 12; k++) o.w[k] = 65535u;           /* lo = 65535, hi = 0: no ray enters */
+    for (int k = 0; k < 4; k++) o.c[k] = RR_REF_EMPTY;
+    for (int side = 0; side < 2; side++) {
+        const uint32_t ref = side ? nd.c1 : nd.c0;
+        const uint32_t* wb = nd.w + 3 * side;
+        if (ref & RR_REF_LEAF) {                            /* a leaf (or an absent child) keeps its own box and slot */
+            for (int a = 0; a < 3; a++) o.w[6 * side + a] = wb[a];
+            o.c[2 * side] = ref;
+        } else {
+            const RRNode ch = bin[ref];
+            for (int k = 0; k < 6; k++) o.w[6 * side + k] = ch.w[k];
+            o.c[2 * side] = (ch.c0 & RR_REF_LEAF) ? ch.c0 : widx[ch.c0];
+            o.c[2 * side + 1] = (ch.c1 & RR_REF_LEAF) ? ch.c1 : widx[ch.c1];
+        }
+    }
+    out[widx[i]] = o;
 }
 
 __global__ void k_pack_tris(const float4* __restrict__ tri, const uint32_t* __restrict__ order, const uint32_t* __restrict__ obj,
@@ -573,12 +601,22 @@ int rr_bvh_build_device(const float* verts, size_t n_verts, const uint32_t* tri_
         RRPackedBVH h;
         rr_bvh_build_host(soup, nodes, order);
         rr_bvh_pack(soup, nodes, order, h);
+#if RR_WIDE_BVH
+        std::vector<RRNode4> wide;
+        rr_bvh_widen_host(h.nodes, wide);
+        BCK(cudaMalloc((void**)&out.d_nodes, std::max<size_t>(1, wide.size()) * sizeof(RRNode4)));
+        BCK(cudaMalloc((void**)&out.d_tris, std::max<size_t>(1, h.tris.size()) * sizeof(float4)));
+        BCK(cudaMemcpy(out.d_nodes, wide.data(), wide.size() * sizeof(RRNode4), cudaMemcpyHostToDevice));
+        const size_t n_packed = wide.size();
+#else
         BCK(cudaMalloc((void**)&out.d_nodes, std::max<size_t>(1, h.nodes.size()) * sizeof(RRNode)));
         BCK(cudaMalloc((void**)&out.d_tris, std::max<size_t>(1, h.tris.size()) * sizeof(float4)));
         BCK(cudaMemcpy(out.d_nodes, h.nodes.data(), h.nodes.size() * sizeof(RRNode), cudaMemcpyHostToDevice));
+        const size_t n_packed = h.nodes.size();
+#endif
         if (!h.tris.empty()) BCK(cudaMemcpy(out.d_tris, h.tris.data(), h.tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
         BCK(cudaDeviceSynchronize());
-        out.n_nodes = h.nodes.size(); out.root_ref = h.root_ref; out.max_depth = h.max_depth;
+        out.n_nodes = n_packed; out.root_ref = h.root_ref; out.max_depth = h.max_depth;
         for (int a = 0; a < 3; a++) { out.grid_origin[a] = h.grid_origin[a]; out.grid_scale[a] = h.grid_scale[a]; }
         out.build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return RR_OK;
@@ -677,17 +715,44 @@ int rr_bvh_build_device(const float* verts, size_t n_verts, const uint32_t* tri_
     const int gn = (n_bn + BLD_BLOCK - 1) / BLD_BLOCK;
     k_parents<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_parent);
     k_subtree_counts<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_parent, d_done, d_cnt);
-    k_dfs_index<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_parent, d_cnt, d_pidx, d_counters + 3);
-    BCK(cudaGetLastError());
     uint32_t n_inner = 0;
     BCK(cudaMemcpy(&n_inner, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost));       /* inner nodes under (and including) the root */
+    uint32_t *d_kept = nullptr, *d_widx = nullptr;
+#if RR_WIDE_BVH
+    BCK(db.alloc(&d_kept, (size_t)n_inner)); BCK(db.alloc(&d_widx, (size_t)n_inner));
+#endif
+    k_dfs_index<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_parent, d_cnt, d_pidx, d_counters + 3, d_kept);
+    BCK(cudaGetLastError());
     BCK(cudaMalloc((void**)&out.d_nodes, std::max<size_t>(1, n_inner) * sizeof(RRNode)));
     BCK(cudaMalloc((void**)&out.d_tris, (size_t)3 * n * sizeof(float4)));
     k_pack_nodes<<<gn, BLD_BLOCK>>>(d_nodes, n_bn, d_pidx, g, out.d_nodes);
     k_pack_tris<<<gb, BLD_BLOCK>>>(d_tri, d_idx[cur], d_obj, n, out.d_tris);
     BCK(cudaGetLastError());
+    out.n_nodes = n_inner;
+#if RR_WIDE_BVH
+    {   /* fold every second level into its parent: prefix of the kept flags = index of the wide node */
+        const int ni = (int)n_inner, sb = (ni + SCAN_TILE - 1) / SCAN_TILE;
+        uint32_t* d_bs;
+        BCK(db.alloc(&d_bs, (size_t)sb + 1));
+        k_scan_reduce<<<sb, BLD_BLOCK>>>(d_kept, ni, d_bs);
+        k_scan_sums<<<1, BLD_BLOCK>>>(d_bs, sb);
+        k_scan_final<<<sb, BLD_BLOCK>>>(d_kept, ni, d_bs, d_widx);
+        uint32_t last_idx = 0, last_kept = 0;
+        BCK(cudaMemcpy(&last_idx, d_widx + (ni - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        BCK(cudaMemcpy(&last_kept, d_kept + (ni - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        const uint32_t n_wide = last_idx + last_kept;
+        RRNode4* d_wide;
+        BCK(cudaMalloc((void**)&d_wide, std::max<size_t>(1, n_wide) * sizeof(RRNode4)));
+        k_widen<<<(ni + BLD_BLOCK - 1) / BLD_BLOCK, BLD_BLOCK>>>(out.d_nodes, ni, d_kept, d_widx, d_wide);
+        BCK(cudaGetLastError());
+        BCK(cudaDeviceSynchronize());
+        cudaFree(out.d_nodes);
+        out.d_nodes = reinterpret_cast<RRNode*>(d_wide);
+        out.n_nodes = n_wide;
+    }
+#endif
     BCK(cudaMemcpy(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost));   /* also waits for the pack kernels */
-    out.n_nodes = n_inner; out.root_ref = 0; out.max_depth = counters[3];
+    out.root_ref = 0; out.max_depth = counters[3];
     out.build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (getenv("RR_VERBOSE")) fprintf(stderr, "[rr_bvh] device build: %d tris, %d build nodes, %u packed nodes, depth %d, %d levels, %d small subtrees, %.1f ms tree + pack = %.1f ms\n",
                                       n, n_bn, n_inner, out.max_depth, levels, n_small, dev_ms, out.build_ms);

@@ -26,6 +26,22 @@ struct __attribute__((aligned(32))) RRNode {
     uint32_t w[6];       /* (lo | hi << 16) for child0 x,y,z then child1 x,y,z */
     uint32_t c0, c1;
 };
+/* RR_WIDE_BVH = 1 (build variant): 4-wide nodes of 64 bytes, made by folding every second level of the binary tree into
+ * its parent (the children of a node's inner children become its children; a leaf child keeps its slot, the slot next to
+ * it stays empty). Same quantisation and plane layout, child k in w[3k .. 3k+2]; an empty slot has an inverted box and
+ * RR_REF_EMPTY. One step then decides four boxes and the walk takes about half as many dependent steps. */
+#ifndef RR_WIDE_BVH
+#define RR_WIDE_BVH 0
+#endif
+struct __attribute__((aligned(64))) RRNode4 {
+    uint32_t w[12];      /* (lo | hi << 16): child k axis a in w[3 * k + a] */
+    uint32_t c[4];
+};
+#if RR_WIDE_BVH
+#define RR_NODE_BYTES 64
+#else
+#define RR_NODE_BYTES 32
+#endif
 #define RR_REF_LEAF   0x80000000u
 #define RR_REF_EMPTY  0xffffffffu
 #ifndef RR_MAX_LEAF

@@ -176,6 +176,41 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
      * lanes of the warp reconverge after the inner loop, so the triangle tests below run once per round with (nearly)
      * all lanes on a leaf instead of being replayed for one or two lanes between node steps. RR_REF_EMPTY (which has
      * the leaf bit set, so it also ends the inner loop) marks a finished lane. */
+#if RR_WIDE_BVH
+    /* one step over a 4-wide node: four boxes, the hit children sorted by entry distance (keys of missed children are
+     * +inf), next = nearest, the others postponed far to near */
+    auto node_step = [&]() {
+        const uint4* np = reinterpret_cast<const uint4*>(reinterpret_cast<const RRNode4*>(nodes) + cur);
+        const uint4 A = __ldg(np), B = __ldg(np + 1), C = __ldg(np + 2);     /* c0.xyz c1.x | c1.yz c2.xy | c2.z c3.xyz */
+        const uint4 R = __ldg(np + 3);
+        if (STATS) n_nodes++;
+#define RR_BOX(wx, wy, wz, key) do { \
+            const float tn_ = fmaxf(fmaxf(fmaf(rr_plane(wx, nx, magic), sax, sbx), fmaf(rr_plane(wy, ny, magic), say, sby)), \
+                                    fmaxf(fmaf(rr_plane(wz, nz, magic), saz, sbz), 0.0f)); \
+            const float tf_ = fminf(fminf(fmaf(rr_plane(wx, fx, magic), sax, sbx), fmaf(rr_plane(wy, fy, magic), say, sby)), \
+                                    fminf(fmaf(rr_plane(wz, fz, magic), saz, sbz), limit)); \
+            key = (tn_ <= tf_) ? tn_ : INFINITY; } while (0)
+        float k0, k1, k2, k3;
+        RR_BOX(A.x, A.y, A.z, k0);
+        RR_BOX(A.w, B.x, B.y, k1);
+        RR_BOX(B.z, B.w, C.x, k2);
+        RR_BOX(C.y, C.z, C.w, k3);
+#undef RR_BOX
+        uint32_t r0 = R.x, r1 = R.y, r2 = R.z, r3 = R.w;
+#define RR_CE(ka, ra, kb, rb) do { const bool sw_ = kb < ka; const float kt_ = sw_ ? kb : ka; kb = sw_ ? ka : kb; ka = kt_; \
+                                   const uint32_t rt_ = sw_ ? rb : ra; rb = sw_ ? ra : rb; ra = rt_; } while (0)
+        RR_CE(k0, r0, k1, r1); RR_CE(k2, r2, k3, r3); RR_CE(k0, r0, k2, r2); RR_CE(k1, r1, k3, r3); RR_CE(k1, r1, k2, r2);
+#undef RR_CE
+        if (k0 < INFINITY) {
+            if (k3 < INFINITY) RR_PUSH(r3);
+            if (k2 < INFINITY) RR_PUSH(r2);
+            if (k1 < INFINITY) RR_PUSH(r1);
+            cur = r0;
+        } else {
+            cur = RR_POP();
+        }
+    };
+#else
     /* one node step of this lane's ray: both child boxes, next = nearer hit child, the other one postponed */
     auto node_step = [&]() {
 #if RR_LDG256
@@ -227,6 +262,7 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
             cur = RR_POP();
         }
     };
+#endif
     /* the triangles of the leaf `cur` holds, then the next postponed subtree */
     auto leaf_step = [&]() {
         const uint32_t first = cur & 0x0fffffffu;
@@ -266,6 +302,122 @@ __device__ __forceinline__ int rr_trace(const RRNode* __restrict__ nodes, const 
     t_hit = best_t;
     face_hit = best_face;
     return best_slot;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Two rays per lane (RR_DUAL, rr_dual_kernel): the walk of one ray is a chain of dependent steps (node load -> planes ->
+ * min/max -> compare -> next ref), and the wide-BVH experiment showed that the chain, not the instruction count, sets
+ * its pace. A warp therefore walks TWO groups at once: every lane carries ray A (group 2p) and ray B (group 2p + 1), and
+ * one straight-line, branch-free step advances both — two independent chains the scheduler can interleave. A ray that
+ * already holds a leaf (or is finished) takes the step on the root node and discards it. Each ray keeps its own order of
+ * nodes and triangles, so hits and counters are those of rr_trace.
+ * ---------------------------------------------------------------------------------------------- */
+struct RRWalk {
+    float sax, say, saz, sbx, sby, sbz;
+    uint32_t nx, ny, nz;
+    float limit;
+    uint32_t cur;
+    int sp;
+    float best_t;
+    int best_face, best_slot;
+    rr_vec3 o, d;
+};
+
+__device__ __forceinline__ void rr_walk_init(RRWalk& W, const float* go, const float* gs, rr_vec3 o, rr_vec3 d, float tmax,
+                                             uint32_t root_ref, bool valid, uint32_t* stack)
+{
+    const float ix = rr_safe_rcp(d.x), iy = rr_safe_rcp(d.y), iz = rr_safe_rcp(d.z);
+    W.sax = gs[0] * ix; W.say = gs[1] * iy; W.saz = gs[2] * iz;
+    W.sbx = fmaf(-8388608.0f, W.sax, (go[0] - o.x) * ix);
+    W.sby = fmaf(-8388608.0f, W.say, (go[1] - o.y) * iy);
+    W.sbz = fmaf(-8388608.0f, W.saz, (go[2] - o.z) * iz);
+    W.nx = (ix >= 0.f) ? 0x7610u : 0x7632u;
+    W.ny = (iy >= 0.f) ? 0x7610u : 0x7632u;
+    W.nz = (iz >= 0.f) ? 0x7610u : 0x7632u;
+    W.limit = tmax * 1.00001f + 1e-6f;
+    W.cur = valid ? root_ref : RR_REF_EMPTY;
+    stack[0] = RR_REF_EMPTY;                       /* sentinel: popping it ends the walk */
+    W.sp = 1;
+    W.best_t = INFINITY; W.best_face = -1; W.best_slot = -1;
+    W.o = o; W.d = d;
+}
+
+/* one branch-free node step of ray W (a no-op on the ray's state when `inner` is false) */
+template <bool STATS>
+__device__ __forceinline__ void rr_walk_step(RRWalk& W, const bool inner, const RRNode* __restrict__ nodes, const uint32_t magic,
+                                             uint32_t* stack, unsigned& n_nodes)
+{
+    const uint4* np = reinterpret_cast<const uint4*>(nodes + (inner ? W.cur : 0u));
+    const uint4 a = __ldg(np);
+    const uint4 b = __ldg(np + 1);
+    if (STATS) n_nodes += inner ? 1u : 0u;
+    const uint32_t fx = W.nx ^ 0x0022u, fy = W.ny ^ 0x0022u, fz = W.nz ^ 0x0022u;
+    const float t0n = fmaxf(fmaxf(fmaf(rr_plane(a.x, W.nx, magic), W.sax, W.sbx), fmaf(rr_plane(a.y, W.ny, magic), W.say, W.sby)),
+                            fmaxf(fmaf(rr_plane(a.z, W.nz, magic), W.saz, W.sbz), 0.0f));
+    const float t0f = fminf(fminf(fmaf(rr_plane(a.x, fx, magic), W.sax, W.sbx), fmaf(rr_plane(a.y, fy, magic), W.say, W.sby)),
+                            fminf(fmaf(rr_plane(a.z, fz, magic), W.saz, W.sbz), W.limit));
+    const float t1n = fmaxf(fmaxf(fmaf(rr_plane(a.w, W.nx, magic), W.sax, W.sbx), fmaf(rr_plane(b.x, W.ny, magic), W.say, W.sby)),
+                            fmaxf(fmaf(rr_plane(b.y, W.nz, magic), W.saz, W.sbz), 0.0f));
+    const float t1f = fminf(fminf(fmaf(rr_plane(a.w, fx, magic), W.sax, W.sbx), fmaf(rr_plane(b.x, fy, magic), W.say, W.sby)),
+                            fminf(fmaf(rr_plane(b.y, fz, magic), W.saz, W.sbz), W.limit));
+    const bool h0 = (t0n <= t0f), h1 = (t1n <= t1f);
+    const bool first0 = (t0n <= t1n);
+    const uint32_t near_ref = first0 ? b.z : b.w, far_ref = first0 ? b.w : b.z;      /* when both children are hit */
+    const bool both = inner && h0 && h1, none = inner && !(h0 || h1);
+    uint32_t nxt = h0 ? (h1 ? near_ref : b.z) : b.w;
+    if (both) { stack[W.sp] = far_ref; W.sp++; }
+    if (none) { W.sp--; nxt = stack[W.sp]; }
+    W.cur = inner ? nxt : W.cur;
+}
+
+/* the triangles of the leaf W.cur holds, then the next postponed subtree */
+template <bool STATS>
+__device__ __forceinline__ void rr_walk_leaf(RRWalk& W, const float4* __restrict__ tris, const float tmax, uint32_t* stack, unsigned& n_tris)
+{
+    const uint32_t first = W.cur & 0x0fffffffu;
+    const uint32_t cnt = ((W.cur >> 28) & 7u) + 1u;
+    for (uint32_t k = 0; k < cnt; k++) {
+        const float4 q0 = __ldg(tris + 3 * (first + k));
+        const float4 q1 = __ldg(tris + 3 * (first + k) + 1);
+        const float4 q2 = __ldg(tris + 3 * (first + k) + 2);
+        if (STATS) n_tris++;
+        float t;
+        if (rr_ray_triangle(W.o, W.d, rr_v3(q0.x, q0.y, q0.z), rr_v3(q1.x, q1.y, q1.z), rr_v3(q2.x, q2.y, q2.z), tmax, &t)) {
+            const int face = (int)__float_as_uint(q0.w);
+            if (W.best_face < 0 || t < W.best_t || (t == W.best_t && face < W.best_face)) {
+                W.best_t = t; W.best_face = face; W.best_slot = (int)(first + k);
+                W.limit = W.best_t * 1.00001f + 1e-6f;
+            }
+        }
+    }
+    W.sp--;
+    W.cur = stack[W.sp];
+}
+
+template <bool STATS>
+__device__ __forceinline__ void rr_trace2(const RRNode* __restrict__ nodes, const float4* __restrict__ tris, uint32_t root_ref,
+                                          const float* go, const float* gs, const float tmax,
+                                          rr_vec3 oA, rr_vec3 dA, bool validA, rr_vec3 oB, rr_vec3 dB, bool validB,
+                                          int2& hitA, int2& hitB, unsigned& n_nodes, unsigned& n_tris)
+{
+    uint32_t stackA[RR_STACK_SIZE + 1], stackB[RR_STACK_SIZE + 1];
+    RRWalk A, B;
+    rr_walk_init(A, go, gs, oA, dA, tmax, root_ref, validA, stackA);
+    rr_walk_init(B, go, gs, oB, dB, tmax, root_ref, validB, stackB);
+    uint32_t magic;
+    asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));
+    while (A.cur != RR_REF_EMPTY || B.cur != RR_REF_EMPTY) {
+        bool inA = !(A.cur & RR_REF_LEAF), inB = !(B.cur & RR_REF_LEAF);
+        while (inA || inB) {
+            rr_walk_step<STATS>(A, inA, nodes, magic, stackA, n_nodes);
+            rr_walk_step<STATS>(B, inB, nodes, magic, stackB, n_nodes);
+            inA = !(A.cur & RR_REF_LEAF); inB = !(B.cur & RR_REF_LEAF);
+        }
+        if (A.cur != RR_REF_EMPTY) rr_walk_leaf<STATS>(A, tris, tmax, stackA, n_tris);
+        if (B.cur != RR_REF_EMPTY) rr_walk_leaf<STATS>(B, tris, tmax, stackB, n_tris);
+    }
+    hitA = make_int2(A.best_slot, __float_as_int(A.best_t));
+    hitB = make_int2(B.best_slot, __float_as_int(B.best_t));
 }
 
 /* Ken Perlin's reference permutation (image_algorithms.h:14-50 holds it twice back to back) */
@@ -397,7 +549,7 @@ __global__ void __launch_bounds__(128) rr_mat_pairs_kernel(const float4* __restr
  * (closest hit -> hit_rec[j] = (triangle slot, range)) with the small register budget of the walk, rr_shade_kernel reads
  * the hit records and does everything after the cast with the registers the fp64 shading wants. Same code, same order,
  * same bits; which form runs is a host-side switch (rr_api.cu). */
-enum { RR_PASS_FUSED = 0, RR_PASS_WALK = 1, RR_PASS_SHADE = 2 };
+enum { RR_PASS_FUSED = 0, RR_PASS_WALK = 1, RR_PASS_SHADE = 2, RR_PASS_DUAL = 3 };
 template <bool STATS, bool DEBUG, int MODE>
 __device__ __forceinline__ void rr_pass_body(const RRFrameParams& P, const int pass, uint32_t* s_trace_stack)
 {
@@ -429,11 +581,56 @@ __device__ __forceinline__ void rr_pass_body(const RRFrameParams& P, const int p
     unsigned stat_nodes = 0, stat_tris = 0;
     uint32_t warp_casts = 0, warp_hits = 0, warp_sigs = 0;
 
+    /* map-frame ray of list position jj (what the cast needs of a wave): RR_PASS_DUAL walks two groups before it shades them */
+    auto ray_of = [&](const uint32_t jj, const uint32_t gq, rr_vec3& o_m, rr_vec3& d_m) {
+        rr_vec3 wo, wd; uint32_t it;
+        if (pass == 0) {
+            it = jj / S;
+            const uint32_t smp = jj - it * S;
+            const float* bd = P.beam_dirs + (P.beam_stride ? (size_t)(it / (uint32_t)P.az_count) * P.beam_stride : (size_t)0);
+            wo = rr_v3(0.f, 0.f, 0.f);
+            wd = rr_v3(bd[3 * smp], bd[3 * smp + 1], bd[3 * smp + 2]);
+        } else {
+            uint32_t gg = P.first_src[gq];
+            while (gbase[gg + 1] <= jj) gg++;
+            const size_t slot = (size_t)gg * 64u + (jj - gbase[gg]);
+            wo = rr_v3(__ldg(cf + 0 * sc + slot), __ldg(cf + 1 * sc + slot), __ldg(cf + 2 * sc + slot));
+            wd = rr_v3(__ldg(cf + 3 * sc + slot), __ldg(cf + 4 * sc + slot), __ldg(cf + 5 * sc + slot));
+            it = __ldg(ci + slot);
+        }
+        const float4 xr = __ldg(P.item_xf + 3 * (size_t)it), xt = __ldg(P.item_xf + 3 * (size_t)it + 1);
+        rr_quat R; R.x = xr.x; R.y = xr.y; R.z = xr.z; R.w = xr.w;
+        if (pass == 0) { const float4 x0 = __ldg(P.item_xf + 3 * (size_t)it + 2); o_m = rr_v3(x0.x, x0.y, x0.z); }
+        else o_m = rr_add(RR_QROT(R, wo), rr_v3(xt.x, xt.y, xt.z));
+        d_m = RR_QROT(R, wd);
+    };
+    uint32_t pair_g = 0, pair_left = 0;
     while (true) {
         uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(P.work_counter + (MODE == RR_PASS_SHADE ? RR_MAX_PASSES + 1 : 0) + pass, 1u);
-        g = __shfl_sync(RR_FULL, g, 0);
-        if (g >= n_groups) break;
+        if (MODE == RR_PASS_DUAL) {
+            if (pair_left == 0u) {                         /* next pair of groups: walk both, then shade them one by one */
+                if (lane == 0) pair_g = atomicAdd(P.work_counter + pass, 2u);
+                pair_g = __shfl_sync(RR_FULL, pair_g, 0);
+                if (pair_g >= n_groups) break;
+                const uint32_t jA = pair_g * 32u + (uint32_t)lane, jB = jA + 32u;
+                const bool vA = jA < n_in, vB = jB < n_in;
+                rr_vec3 oA = rr_v3(0.f, 0.f, 0.f), dA = rr_v3(1.f, 0.f, 0.f), oB = oA, dB = dA;
+                if (vA) ray_of(jA, pair_g, oA, dA);
+                if (vB) ray_of(jB, pair_g + 1u, oB, dB);
+                int2 hA, hB;
+                rr_trace2<STATS>(P.nodes, P.tris, P.root_ref, go, gs, 1000.0f, oA, dA, vA, oB, dB, vB, hA, hB, stat_nodes, stat_tris);
+                if (vA) P.hit_rec[jA] = hA;                /* read back by this very thread below */
+                if (vB) P.hit_rec[jB] = hB;
+                pair_left = 2u;
+            }
+            g = pair_g + (2u - pair_left);
+            pair_left--;
+            if (g >= n_groups) continue;
+        } else {
+            if (lane == 0) g = atomicAdd(P.work_counter + (MODE == RR_PASS_SHADE ? RR_MAX_PASSES + 1 : 0) + pass, 1u);
+            g = __shfl_sync(RR_FULL, g, 0);
+            if (g >= n_groups) break;
+        }
         const uint32_t j = g * 32u + (uint32_t)lane;
         const bool active = j < n_in;
         const uint32_t act_mask = __ballot_sync(RR_FULL, active);
@@ -481,8 +678,8 @@ __device__ __forceinline__ void rr_pass_body(const RRFrameParams& P, const int p
             else o_m = rr_add(RR_QROT(R, w.o), rr_v3(xt.x, xt.y, xt.z));
             const rr_vec3 d_m = RR_QROT(R, w.d);
             int slot_t;
-            if (MODE == RR_PASS_SHADE) {
-                const int2 hr = __ldcs(P.hit_rec + j);
+            if (MODE == RR_PASS_SHADE || MODE == RR_PASS_DUAL) {
+                const int2 hr = (MODE == RR_PASS_DUAL) ? P.hit_rec[j] : __ldcs(P.hit_rec + j);
                 slot_t = hr.x; range = __int_as_float(hr.y);
                 if (DEBUG && slot_t >= 0) face = (int)__float_as_uint(__ldg(P.tris + 3 * slot_t).w);
             } else {
@@ -680,6 +877,14 @@ __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_WALK_MIN_BLOCKS) rr_walk_ke
 {
     extern __shared__ uint32_t s_trace_stack[];
     rr_pass_body<STATS, false, RR_PASS_WALK>(P, pass, s_trace_stack);
+}
+#ifndef RR_DUAL_MIN_BLOCKS
+#define RR_DUAL_MIN_BLOCKS 6       /* resident 128-thread CTAs per SM of the two-rays-per-lane kernel (80 registers) */
+#endif
+template <bool STATS, bool DEBUG>
+__global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_DUAL_MIN_BLOCKS) rr_dual_kernel(const RRFrameParams P, const int pass)
+{
+    rr_pass_body<STATS, DEBUG, RR_PASS_DUAL>(P, pass, nullptr);
 }
 template <bool DEBUG>
 __global__ void __launch_bounds__(RR_TRACE_BLOCK, RR_SHADE_MIN_BLOCKS) rr_shade_kernel(const RRFrameParams P, const int pass)
@@ -1358,6 +1563,19 @@ extern "C" cudaError_t rr_split_occupancy(int* walk_blocks_per_sm, int* shade_bl
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(walk_blocks_per_sm, rr_walk_kernel<false>, RR_TRACE_BLOCK, RR_TRACE_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, rr_shade_kernel<false>, RR_TRACE_BLOCK, 0);
+}
+
+extern "C" cudaError_t rr_dual_occupancy(int* blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rr_dual_kernel<false, false>, RR_TRACE_BLOCK, 0);
+}
+
+extern "C" cudaError_t rr_launch_dual(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats, int debug)
+{
+    if (debug) rr_dual_kernel<true, true><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    else if (stats) rr_dual_kernel<true, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    else rr_dual_kernel<false, false><<<grid, RR_TRACE_BLOCK, 0, st>>>(*P, pass);
+    return cudaGetLastError();
 }
 
 extern "C" cudaError_t rr_launch_walk(const RRFrameParams* P, int pass, int grid, cudaStream_t st, int stats)

@@ -154,24 +154,29 @@ def test_row_major_output_paths_equal_the_oracle(oracle_mod, n_cells):
             assert np.array_equal(imgs[i], o["image"]), "n_cells %d scroll %d pose %d" % (n_cells, scroll, i)
 
 
-def test_pass_as_two_kernels_matches_the_fused_kernel(oracle_mod, monkeypatch):
-    """RR_PASS_SPLIT=1 (read when a context first sizes its scratch): every pass runs as rr_walk_kernel (cast only, hit
-    records) + rr_shade_kernel instead of the fused rr_trace_kernel. Same images, same counters, same debug records."""
+@pytest.mark.parametrize("switch", ["RR_PASS_SPLIT", "RR_PASS_DUAL"])
+def test_alternative_pass_kernels_match_the_fused_kernel(oracle_mod, monkeypatch, switch):
+    """RR_PASS_SPLIT=1: every pass runs as rr_walk_kernel (cast only, hit records) + rr_shade_kernel; RR_PASS_DUAL=1: as
+    rr_dual_kernel (two rays per lane, both walks advanced by one branch-free step). Both are measured alternatives to
+    the fused rr_trace_kernel read when a context first sizes its scratch. Same images, same counters."""
     sc = scenes.warehouse_small()
     cfg = RadarModelConfig(**dict(MULRAN_DYNCFG, n_samples=37, n_reflections=4, n_cells=900, resolution=0.03,
                                   record_multi_path=1, record_multi_reflection=1))
     poses = sc.pose_array(3)
     out = {}
-    for split in ("0", "1"):
-        monkeypatch.setenv("RR_PASS_SPLIT", split)
+    monkeypatch.delenv("RR_PASS_SPLIT", raising=False)
+    monkeypatch.delenv("RR_PASS_DUAL", raising=False)
+    for on in ("0", "1"):
+        monkeypatch.setenv(switch, on)
         radar = RadarB200(sc, cfg, beam_seed=3, noise_seed=4)
         radar.setMaxWavesPerAzimuth(37 * 16)
         img = radar.simulate(poses, frame_id=9).copy()
         one, st = radar.simulate_stats(poses[1], frame_id=10)
-        out[split] = (img, one, (st.n_casts, st.n_hits, st.n_signals, st.nodes_visited, st.tris_tested), radar.kernel_launches())
+        out[on] = (img, one, (st.n_casts, st.n_hits, st.n_signals, st.nodes_visited, st.tris_tested), radar.kernel_launches())
     assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
     assert out["0"][2] == out["1"][2]
-    assert out["1"][3] > out["0"][3], "the split form launches one more kernel per pass"
+    if switch == "RR_PASS_SPLIT":
+        assert out["1"][3] > out["0"][3], "the split form launches one more kernel per pass"
     o = oracle_mod.OracleScene(sc).simulate(cfg, radar.getBeamSamples(), poses[1:2], noise_seed=4, frame_id=10)
     assert np.array_equal(out["1"][1], o["image"])
 
