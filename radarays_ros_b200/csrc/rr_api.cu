@@ -743,7 +743,7 @@ static int ensure_scratch(rr_ctx* ctx, size_t want_items)
     /* longest per-azimuth wave list a pass may reach: user value, else room for 3 dielectric splits per path */
     uint32_t wpi = ctx->max_waves_user ? ctx->max_waves_user : S * (1u << std::min<uint32_t>(Pn - 1, 3));
     wpi = std::max<uint32_t>(wpi, S);
-    const size_t per_wave = 2 /*buffers*/ * 2 /*slots*/ * 48 + (size_t)Pn * 16 + 2;
+    const size_t per_wave = 2 /*buffers*/ * 2 /*slots*/ * 48 + (size_t)Pn * 16 + 8 /*hit record*/ + 2;
     const size_t per_item = (size_t)wpi * per_wave + (size_t)(Pn + 1) * 4;
     size_t max_items = std::max<size_t>(RR_N_ANGLES, ((size_t)4 << 30) / per_item);
     max_items = std::min<size_t>(max_items, std::max<size_t>(want_items, RR_N_ANGLES));
