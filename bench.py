@@ -274,7 +274,7 @@ def main():
     if args.steps is not None:
         K = args.steps
     else:
-        K = {2: 250, 3: 60, 4: 150, 5: 3}[args.config] if args.impl == "b200" else 10
+        K = {2: 300, 3: 80, 4: 150, 5: 3}[args.config] if args.impl == "b200" else 10
     noise_seed, beam_seed = 20240310, 20240310
 
     # ------------------------------------------------------------------------------------------ reference arm
