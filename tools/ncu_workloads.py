@@ -45,6 +45,10 @@ def run(wl_list, scene):
 
 def main():
     small = "--small" in sys.argv
+    if "--config2-only" in sys.argv:                       # launch lists of the alternative walk kernels (tools/gpu_alt_launches.sh)
+        w2 = Workload(2, small)
+        run([w2], w2.make_scene())
+        return
     urban = [Workload(2, small)] + [Workload(3, small, samples=s) for s in (64, 128, 256, 512, 1024, 2048)]
     run(urban, urban[0].make_scene())
     w4 = Workload(4, small)
